@@ -81,6 +81,7 @@ uint32_t nhash(const void *key, size_t length, uint32_t initval);
 
 /* ---- intermediates the reference keeps private inside wspr_decode (exposed for stage-level parity) ---- */
 void oracle_mettab(int mettab[2][256]);                                   /* wsprd.c:467-473 (derived ints) */
+void oracle_window(float *win /*[512]*/);                                /* wsprd.c:510-513 */
 int oracle_blocks(int samples);                                           /* wsprd.c:516 */
 void oracle_spectrogram(const float *idat, const float *qdat, int samples, float *ps /*[512][blocks]*/);
 /* candidate finder + coarse sync of one pass (wsprd.c:555-678); returns npk, fills cands[<=200] */
