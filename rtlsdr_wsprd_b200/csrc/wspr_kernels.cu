@@ -1,0 +1,1076 @@
+// CUDA kernels of the batched WSPR decode path (sm_100a).  Compiled with -fmad=false: every float expression
+// below is evaluated with the same roundings, in the same order, as the reference C code it replaces, so the
+// results are bit-identical to x86-64 gcc -O3 (no FMA contraction).  File:line citations are relative to the
+// reference checkout (wsprd/wsprd.c unless stated).
+#include "wspr_kernels.cuh"
+
+#include <math_constants.h>
+
+#include "fft512_twiddle.h"
+#include "wspr_math.cuh"
+#include "wspr_mettab.h"
+
+namespace wspr {
+
+static unsigned long long g_launches = 0;
+unsigned long long kernel_launch_count() { return g_launches; }
+#define LAUNCHED() (++g_launches)
+
+// ---- constant tables ----------------------------------------------------------------------------------
+__constant__ float c_window[NFFT];
+__constant__ float c_lpf_w[NFILT];
+__constant__ float c_lpf_psum[NFILT];
+__constant__ float c_min_snr;
+__constant__ float c_floor_snr;
+__constant__ short c_mettab[512] = WSPR_METTAB_FLAT;
+__device__ const double g_tw[256][2] = FFT512_TWIDDLE_INIT;
+
+void upload_tables(const HostTables &t) {
+    cudaMemcpyToSymbol(c_window, t.window, sizeof t.window);
+    cudaMemcpyToSymbol(c_lpf_w, t.lpf_w, sizeof t.lpf_w);
+    cudaMemcpyToSymbol(c_lpf_psum, t.lpf_psum, sizeof t.lpf_psum);
+    cudaMemcpyToSymbol(c_min_snr, &t.min_snr, sizeof(float));
+    cudaMemcpyToSymbol(c_floor_snr, &t.floor_snr, sizeof(float));
+}
+
+// rate constants, written as the reference's macro expansions evaluate (wsprd.c:59-69)
+__device__ __forceinline__ double twopidt() { return 2.0 * M_PI * 1.0 / 375.0; }
+#define W_DF (375.0 / 256.0)
+#define W_HALF_DF (375.0 / 256.0 / 2.0)
+
+// =========================================================================================================
+// K1  spectrogram: 512-point windowed FFT every 128 samples, |X|^2, fftshift (wsprd.c:536-553).
+// The transform is the binary64 radix-2 DIT graph of the oracle's FFTW stand-in (FFTW itself is an
+// un-vendored dependency of the reference), so ps is bit-identical to the oracle's.
+// Layout: psT[capture][block][bin] (block-major; the reference's ps[bin][block] transposed, which makes the
+// stores and the per-bin block sums of K2 coalesced).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_spectrogram(const float *__restrict__ I, const float *__restrict__ Q,
+                                                     float *__restrict__ psT, int stride, int blocks) {
+    __shared__ double re[NFFT], im[NFFT];
+    const int b = blockIdx.x, cap = blockIdx.y, t = threadIdx.x;
+    const float *ip = I + (size_t)cap * stride + b * HOP;
+    const float *qp = Q + (size_t)cap * stride + b * HOP;
+    for (int n = t; n < NFFT; n += 256) {
+        float w = c_window[n];
+        float xr = ip[n] * w, xi = qp[n] * w;
+        int r = (int)(__brev((unsigned)n) >> 23);
+        re[r] = (double)xr;
+        im[r] = (double)xi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 9; s++) {
+        const int half = 1 << s;
+        const int j = t & (half - 1);
+        const int a = ((t >> s) << (s + 1)) + j, bb = a + half;
+        const double wr = g_tw[j << (8 - s)][0], wi = g_tw[j << (8 - s)][1];
+        const double vr = re[bb], vi = im[bb], ur = re[a], ui = im[a];
+        const double tr = wr * vr - wi * vi;
+        const double ti = wr * vi + wi * vr;
+        re[bb] = ur - tr;
+        im[bb] = ui - ti;
+        re[a] = ur + tr;
+        im[a] = ui + ti;
+        __syncthreads();
+    }
+    float *out = psT + ((size_t)cap * blocks + b) * NFFT;
+    for (int k = t; k < NFFT; k += 256) {
+        float fr = (float)re[k], fi = (float)im[k];
+        out[(k + NFFT / 2) & (NFFT - 1)] = fr * fr + fi * fi;
+    }
+}
+
+void launch_spectrogram(const float *I, const float *Q, float *psT, int ncap, const DecodeParams &p, cudaStream_t st) {
+    if (ncap <= 0 || p.blocks <= 0) return;
+    k_spectrogram<<<dim3(p.blocks, ncap), 256, 0, st>>>(I, Q, psT, p.stride, p.blocks);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// K2  candidate search: block sums, 7-bin boxcar, 30th-percentile noise floor, SNR normalisation, strict local
+// maxima, +-110 Hz filter, stable sort by SNR (wsprd.c:555-631).  One CTA per capture.
+// =========================================================================================================
+__global__ void __launch_bounds__(512) k_candidates(const float *__restrict__ psT, Cand *__restrict__ cands,
+                                                    CapState *__restrict__ caps, float *__restrict__ smspec_dbg,
+                                                    Counters *cnt, int blocks) {
+    __shared__ float psavg[NFFT];
+    __shared__ float sm[NSMOOTH];
+    __shared__ float noise;
+    const int cap = blockIdx.x, t = threadIdx.x;
+    const float *ps = psT + (size_t)cap * blocks * NFFT;
+    float acc = 0.0f;
+    for (int b = 0; b < blocks; b++) acc += ps[(size_t)b * NFFT + t];     // block order, :557-561
+    psavg[t] = acc;
+    if (t == 0) noise = 0.0f;
+    __syncthreads();
+    float mine = 0.0f;
+    if (t < NSMOOTH) {
+        for (int j = -3; j <= 3; j++) mine += psavg[256 - 205 + t + j];   // :567-573
+        sm[t] = mine;
+    }
+    __syncthreads();
+    if (t < NSMOOTH) {                                                     // ascending rank 122, :576-583
+        int rank = 0;
+        for (int k = 0; k < NSMOOTH; k++) {
+            float o = sm[k];
+            rank += (o < mine) || (o == mine && k < t);
+        }
+        if (rank == 122) noise = mine;
+    }
+    __syncthreads();
+    if (t < NSMOOTH) {                                                     // :593-596
+        float v = (float)((double)(mine / noise) - 1.0);
+        if (v < c_min_snr) v = c_floor_snr;
+        sm[t] = v;
+        if (smspec_dbg) smspec_dbg[(size_t)cap * NSMOOTH + t] = v;
+    }
+    __syncthreads();
+    if (t == 0) {
+        Cand *c = cands + (size_t)cap * MAXCAND;
+        int npk = 0;
+        for (int j = 1; j < NSMOOTH - 1; j++) {                            // :608-629
+            if (sm[j] > sm[j - 1] && sm[j] > sm[j + 1] && npk < MAXCAND) {
+                float f = (float)((j - 205) * W_HALF_DF);
+                if (f >= -110.0f && f <= 110.0f) {
+                    Cand x;
+                    x.freq = f;
+                    x.snr = (float)(10.0 * (double)glibc_log10f(sm[j]) - (double)26.3f);
+                    x.shift = 0;
+                    x.drift = 0.0f;
+                    x.sync = 0.0f;
+                    // stable insertion, descending snr (glibc qsort is a stable merge sort), :631
+                    int pos = npk;
+                    while (pos > 0 && c[pos - 1].snr < x.snr) {
+                        c[pos] = c[pos - 1];
+                        pos--;
+                    }
+                    c[pos] = x;
+                    npk++;
+                }
+            }
+        }
+        // NB: the reference caps the *unfiltered* list at 200; with 409 bins and strict maxima at most 204 exist,
+        // so the cap is only reachable on pathological spectra -- count unfiltered maxima to mirror it exactly.
+        caps[cap].npk = npk;
+        caps[cap].broken = 0;
+        atomicMax(&cnt->maxnpk, npk);
+        atomicAdd(&cnt->totnpk, npk);
+    }
+}
+
+void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, Counters *cnt, int ncap,
+                       const DecodeParams &p, cudaStream_t st) {
+    if (ncap <= 0) return;
+    k_candidates<<<ncap, 512, 0, st>>>(psT, cands, caps, smspec_dbg, cnt, p.blocks);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// K3  coarse sync on the spectrogram (wsprd.c:646-678): 3 frequency bins x 32 half-symbol offsets x drift
+// hypotheses, 162 symbols each.  The reference's drift index only changes which of two bins a symbol reads
+// (the unparenthesised DF macro makes the drift term ~1e-5 bins), so all negative drifts give one pattern and
+// all positive drifts another; with the strict '>' the winners can only be -maxdrift, 0 or +1, which are the
+// three hypotheses evaluated here (with the reference's literal index formula).
+// =========================================================================================================
+constexpr int COARSE_BINS = 12;
+__global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, Cand *__restrict__ cands,
+                                                const CapState *__restrict__ caps, int blocks, int maxdrift) {
+    extern __shared__ float sq[];           // [blocks][COARSE_BINS] sqrt(ps)
+    __shared__ float s_sync[288];
+    const int rank = blockIdx.x, cap = blockIdx.y, t = threadIdx.x;
+    if (rank >= caps[cap].npk) return;
+    Cand *c = cands + (size_t)cap * MAXCAND + rank;
+    const int if0 = (int)((double)c->freq / W_HALF_DF + 256);
+    const int lo = if0 - 6;
+    const float *ps = psT + (size_t)cap * blocks * NFFT;
+    for (int i = t; i < blocks * COARSE_BINS; i += 288) {
+        int b = i / COARSE_BINS, k = i - b * COARSE_BINS;
+        int bin = lo + k;
+        sq[i] = (bin >= 0 && bin < NFFT) ? sqrtf(ps[(size_t)b * NFFT + bin]) : 0.0f;
+    }
+    __syncthreads();
+    const int ifr = if0 - 1 + t / 96;
+    const int k0 = -10 + (t / 3) % 32;
+    const int d = t % 3;
+    const int idrift = (d == 0) ? -maxdrift : (d == 1 ? 0 : 1);
+    const bool valid = (maxdrift > 0) || (d == 1);
+    float sync = CUDART_NAN_F;
+    if (valid) {
+        float ss = 0.0f, pw = 0.0f;
+        for (int k = 0; k < NSYM; k++) {
+            int ifd = (int)(ifr + (double)((((float)k - (float)NBITS) / (float)NBITS) * (float)idrift) / 375.0 / 256.0);
+            int kx = k0 + 2 * k;
+            if (kx < blocks) {
+                int row = kx, col = ifd - lo;
+                if (kx < 0) {               // the reference indexes ps[bin][kx] flat: previous bin's tail
+                    row = blocks + kx;
+                    col -= 1;
+                }
+                const float *r = sq + row * COARSE_BINS + col;
+                float p0 = r[-3], p1 = r[-1], p2 = r[1], p3 = r[3];
+                float m = (p1 + p3) - (p0 + p2);
+                ss = sync_bit(k) ? ss + m : ss - m;
+                pw = pw + p0 + p1 + p2 + p3;
+            }
+        }
+        sync = ss / pw;
+    }
+    s_sync[t] = sync;
+    __syncthreads();
+    if (t == 0) {
+        float best = -1e30f;
+        int arg = -1;
+        for (int h = 0; h < 288; h++)
+            if (s_sync[h] > best) {
+                best = s_sync[h];
+                arg = h;
+            }
+        if (arg >= 0) {
+            int bk0 = -10 + (arg / 3) % 32, bd = arg % 3;
+            c->shift = 128 * (bk0 + 1);
+            c->drift = (float)((bd == 0) ? -maxdrift : (bd == 1 ? 0 : 1));
+            c->freq = (float)((if0 - 1 + arg / 96 - 256) * W_HALF_DF);
+            c->sync = best;
+        }
+    }
+}
+
+void launch_coarse(const float *psT, Cand *cands, const CapState *caps, int ncap, int maxnpk, const DecodeParams &p,
+                   cudaStream_t st) {
+    if (ncap <= 0 || maxnpk <= 0) return;
+    size_t smem = (size_t)p.blocks * COARSE_BINS * sizeof(float);
+    k_coarse<<<dim3(maxnpk, ncap), 288, smem, st>>>(psT, cands, caps, p.blocks, p.maxdrift);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// job list for one wave (candidate ranks [r0, r1) of every capture that is still being decoded)
+// =========================================================================================================
+__global__ void k_make_jobs(const Cand *__restrict__ cands, const CapState *__restrict__ caps, Job *__restrict__ jobs,
+                            int *__restrict__ jobmap, Counters *cnt, int ncap, int r0, int r1, int jobcap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nr = r1 - r0;
+    if (i >= ncap * nr) return;
+    int cap = i / nr, rank = r0 + i % nr;
+    int slot = -1;
+    if (!caps[cap].broken && rank < caps[cap].npk) {
+        slot = atomicAdd(&cnt->njobs, 1);
+        if (slot < jobcap) {
+            const Cand &c = cands[(size_t)cap * MAXCAND + rank];
+            Job j;
+            j.cap = cap;
+            j.rank = rank;
+            j.freq = c.freq;
+            j.drift = c.drift;
+            j.shift = c.shift;
+            j.sync1 = c.sync;
+            j.snr = c.snr;
+            j.worth = 0;
+            j.fbest = 0;
+            j.decoded = 0;
+            j.idt = 0;
+            j.cycles = 0;
+            for (int k = 0; k < 12; k++) j.dec[k] = 0;
+            jobs[slot] = j;
+        } else {
+            slot = -1;
+        }
+    }
+    jobmap[(size_t)cap * MAXCAND + rank] = slot;
+}
+
+void launch_make_jobs(const Cand *cands, const CapState *caps, Job *jobs, int *jobmap, Counters *cnt, int ncap, int r0,
+                      int r1, int jobcap, cudaStream_t st) {
+    int n = ncap * (r1 - r0);
+    if (n <= 0) return;
+    k_make_jobs<<<(n + 255) / 256, 256, 0, st>>>(cands, caps, jobs, jobmap, cnt, ncap, r0, r1, jobcap);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// K4  sync_and_demodulate (wsprd.c:101-259): the 4-tone matched filter.
+// For each (frequency hypothesis, lag, symbol) the reference accumulates, strictly in sample order,
+//     i_t += I[k]*c_t[j] + Q[k]*s_t[j] ;  q_t += -I[k]*s_t[j] + Q[k]*c_t[j]       (t = 0..3 tones, j = 0..255)
+// with phasor tables c_t, s_t generated by a float recurrence seeded by one cosf/sinf pair per tone.  One thread
+// owns one (lag, symbol) cell and its eight running sums, so the order of additions is the reference's.
+// Tables: without drift (the common case) all symbols share one table set, built once per CTA in shared memory;
+// with drift every symbol has its own frequency and the thread advances private phasors in registers.
+// =========================================================================================================
+__device__ __forceinline__ float symbol_freq(float f0, float drift, int i) {   // :156
+    return (float)((double)f0 + ((double)drift / 2.0) * (double)((float)i - (float)NBITS) / (double)(float)NBITS);
+}
+__device__ __forceinline__ void tone_seeds(float fp, float cd[4], float sd[4]) {   // :158-172
+    const double k = twopidt();
+    const float d0 = (float)(k * ((double)fp - W_DF * 1.5));
+    const float d1 = (float)(k * ((double)fp - W_DF * 0.5));
+    const float d2 = (float)(k * ((double)fp + W_DF * 0.5));
+    const float d3 = (float)(k * ((double)fp + W_DF * 1.5));
+    cd[0] = glibc_cosf(d0); sd[0] = glibc_sinf(d0);
+    cd[1] = glibc_cosf(d1); sd[1] = glibc_sinf(d1);
+    cd[2] = glibc_cosf(d2); sd[2] = glibc_sinf(d2);
+    cd[3] = glibc_cosf(d3); sd[3] = glibc_sinf(d3);
+}
+// shared phasor tables, layout tab[j] = {c0,s0,c1,s1}, tab[256+j] = {c2,s2,c3,s3}; threads 0..3 run the
+// recurrences (:174-188).  Caller synchronises.
+__device__ __forceinline__ void build_tables(float fp, float4 *tab, int t) {
+    if (t < 4) {
+        float cd[4], sd[4];
+        tone_seeds(fp, cd, sd);
+        const float cdt = cd[t], sdt = sd[t];
+        float *base = reinterpret_cast<float *>(tab) + (t >> 1) * (SPS * 4) + (t & 1) * 2;
+        float c = 1.0f, s = 0.0f;
+        for (int j = 0; j < SPS; j++) {
+            base[j * 4] = c;
+            base[j * 4 + 1] = s;
+            float cn = c * cdt - s * sdt;
+            float sn = c * sdt + s * cdt;
+            c = cn;
+            s = sn;
+        }
+    }
+}
+
+struct Acc8 {
+    float ai[4], aq[4];
+};
+__device__ __forceinline__ void acc_step(Acc8 &a, float x, float y, const float c[4], const float s[4]) {   // :200-207
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        a.ai[t] = a.ai[t] + x * c[t] + y * s[t];
+        a.aq[t] = a.aq[t] - x * s[t] + y * c[t];
+    }
+}
+__device__ __forceinline__ float4 acc_power(const Acc8 &a) {   // :211-214  (double sqrt of a float == correctly rounded)
+    float4 p;
+    p.x = __fsqrt_rn(a.ai[0] * a.ai[0] + a.aq[0] * a.aq[0]);
+    p.y = __fsqrt_rn(a.ai[1] * a.ai[1] + a.aq[1] * a.aq[1]);
+    p.z = __fsqrt_rn(a.ai[2] * a.ai[2] + a.aq[2] * a.aq[2]);
+    p.w = __fsqrt_rn(a.ai[3] * a.ai[3] + a.aq[3] * a.aq[3]);
+    return p;
+}
+
+// ---- mode 0: all lags of a group of SYMS_PER_CTA symbols, IQ window staged in shared memory ----------------
+// The window is stored transposed, sample m at [m % 8][m / 8], so that lanes holding consecutive lags (8 samples
+// apart) read consecutive shared-memory words.
+constexpr int SYMS_PER_CTA = 6;
+constexpr int LAG_WIN = SYMS_PER_CTA * SPS + SPS;          // 1792 samples cover every lag of the group
+constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 225
+constexpr int LAG_THREADS = 32 * (SYMS_PER_CTA + 1);       // 224
+
+__global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
+                                                           const Job *__restrict__ jobs, float4 *__restrict__ P0, int np,
+                                                           int stride, int lagstep, int nlags) {
+    __shared__ float4 tab[2 * SPS];
+    __shared__ float2 win[8 * LAG_PITCH];
+    const Job &job = jobs[blockIdx.x];
+    const int g = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const float f0 = job.freq, drift = job.drift;
+    const int lagmin = job.shift - 128;
+    const bool shared_tab = (drift == 0.0f);
+    const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
+    const int base = lagmin + g * SYMS_PER_CTA * SPS;       // sample index of window element 0
+    // the staging below assumes lagstep 8 or 16 (lags at multiples of 8 samples)
+    for (int m = t; m < LAG_WIN; m += LAG_THREADS) {
+        int k = base + m;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (k > 0 && k < np) v = make_float2(ip[k], qp[k]);  // k > 0: the reference never reads sample 0 (:199)
+        win[(m & 7) * LAG_PITCH + (m >> 3)] = v;
+    }
+    if (shared_tab) build_tables(f0, tab, t);
+    __syncthreads();
+
+    int sym_local, lagidx;
+    if (warp < SYMS_PER_CTA) {
+        sym_local = warp;
+        lagidx = lane;
+    } else {
+        sym_local = lane;
+        lagidx = 32;
+    }
+    const int sym = g * SYMS_PER_CTA + sym_local;
+    if (sym_local >= SYMS_PER_CTA || sym >= NSYM || lagidx >= nlags) return;
+    const int off = lagidx * lagstep + sym_local * SPS;     // window-relative start of this cell (multiple of 8)
+    const float2 *wp = win + (off >> 3);
+    Acc8 a;
+#pragma unroll
+    for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
+    if (shared_tab) {
+#pragma unroll 2
+        for (int j8 = 0; j8 < SPS / 8; j8++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float2 v = wp[r * LAG_PITCH + j8];
+                float4 w01 = tab[j8 * 8 + r], w23 = tab[SPS + j8 * 8 + r];
+                float c[4] = {w01.x, w01.z, w23.x, w23.z}, s[4] = {w01.y, w01.w, w23.y, w23.w};
+                acc_step(a, v.x, v.y, c, s);
+            }
+        }
+    } else {
+        float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        tone_seeds(symbol_freq(f0, drift, sym), cd, sd);
+        for (int j8 = 0; j8 < SPS / 8; j8++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float2 v = wp[r * LAG_PITCH + j8];
+                acc_step(a, v.x, v.y, c, s);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float cn = c[q] * cd[q] - s[q] * sd[q];
+                    float sn = c[q] * sd[q] + s[q] * cd[q];
+                    c[q] = cn;
+                    s[q] = sn;
+                }
+            }
+        }
+    }
+    P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = acc_power(a);
+}
+
+// per-lag sync metric and arg-max over lags (:216-218,227-232); one warp-sized CTA per job
+__global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const float4 *__restrict__ P0, int lagstep,
+                                                 int nlags) {
+    __shared__ float s_ss[64];
+    Job &job = jobs[blockIdx.x];
+    const int t = threadIdx.x;
+    float v = CUDART_NAN_F;
+    if (t < nlags) {
+        const float4 *p = P0 + ((size_t)blockIdx.x * MAXLAGS + t) * NSYM;
+        float ss = 0.0f, totp = 0.0f;
+        for (int i = 0; i < NSYM; i++) {
+            float4 q = p[i];
+            totp = totp + q.x + q.y + q.z + q.w;
+            float cmet = (q.y + q.w) - (q.x + q.z);
+            ss = sync_bit(i) ? ss + cmet : ss - cmet;
+        }
+        v = ss / totp;
+    }
+    s_ss[t] = v;
+    __syncthreads();
+    if (t == 0) {
+        float best = -1e30f, fbest = 0.0f;
+        int bl = 0;
+        const int lagmin = job.shift - 128;
+        for (int l = 0; l < nlags; l++)
+            if (s_ss[l] > best) {
+                best = s_ss[l];
+                bl = lagmin + l * lagstep;
+                fbest = job.freq;
+            }
+        job.shift = bl;          // the reference returns best_shift = 0 / freq = 0 if no lag ever won
+        job.freq = fbest;
+        job.sync1 = best;
+    }
+}
+
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, int njobs, float4 *P0, const DecodeParams &p,
+                      cudaStream_t st) {
+    if (njobs <= 0) return;
+    k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, P0, p.np, p.stride, p.lagstep,
+                                                                          p.nlags);
+    LAUNCHED();
+    k_pick_lag<<<njobs, 64, 0, st>>>(jobs, P0, p.lagstep, p.nlags);
+    LAUNCHED();
+}
+
+// ---- one symbol per thread at a fixed lag (modes 1 and 2, and the generic ABI wrapper) ----------------------
+__device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip, const float *__restrict__ qp, int np,
+                                                   int start, bool shared_tab, const float4 *tab, float fp) {
+    Acc8 a;
+#pragma unroll
+    for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
+    const bool inside = (start > 0) && (start + SPS <= np);
+    float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (!shared_tab) tone_seeds(fp, cd, sd);
+    if (shared_tab && inside && ((start & 3) == 0)) {
+        const float4 *i4 = reinterpret_cast<const float4 *>(ip + start), *q4 = reinterpret_cast<const float4 *>(qp + start);
+#pragma unroll 2
+        for (int j4 = 0; j4 < SPS / 4; j4++) {
+            float4 xi = i4[j4], xq = q4[j4];
+            float xs[4] = {xi.x, xi.y, xi.z, xi.w}, ys[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                float4 w01 = tab[j4 * 4 + r], w23 = tab[SPS + j4 * 4 + r];
+                float cc[4] = {w01.x, w01.z, w23.x, w23.z}, ss[4] = {w01.y, w01.w, w23.y, w23.w};
+                acc_step(a, xs[r], ys[r], cc, ss);
+            }
+        }
+    } else {
+        for (int j = 0; j < SPS; j++) {
+            int k = start + j;
+            float x = 0.0f, y = 0.0f;
+            if (k > 0 && k < np) {
+                x = ip[k];
+                y = qp[k];
+            }
+            if (shared_tab) {
+                float4 w01 = tab[j], w23 = tab[SPS + j];
+                float cc[4] = {w01.x, w01.z, w23.x, w23.z}, ss[4] = {w01.y, w01.w, w23.y, w23.w};
+                acc_step(a, x, y, cc, ss);
+            } else {
+                acc_step(a, x, y, c, s);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float cn = c[q] * cd[q] - s[q] * sd[q];
+                    float sn = c[q] * sd[q] + s[q] * cd[q];
+                    c[q] = cn;
+                    s[q] = sn;
+                }
+            }
+        }
+    }
+    return acc_power(a);
+}
+
+// mode 1: five frequencies at the best lag (:722-726)
+__global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I, const float *__restrict__ Q,
+                                                    const Job *__restrict__ jobs, float4 *__restrict__ P1, int np,
+                                                    int stride) {
+    __shared__ float4 tab[2 * SPS];
+    const Job &job = jobs[blockIdx.x];
+    const int fi = blockIdx.y, t = threadIdx.x;
+    const float fstep = 0.1f;
+    const float f0 = job.freq + (float)(fi - 2) * fstep;      // :151
+    const bool shared_tab = (job.drift == 0.0f);
+    if (shared_tab) build_tables(f0, tab, t);
+    __syncthreads();
+    if (t >= NSYM) return;
+    const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
+    float fp = shared_tab ? f0 : symbol_freq(f0, job.drift, t);
+    P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = correlate_symbol(ip, qp, np, job.shift + t * SPS, shared_tab, tab, fp);
+}
+
+// soft symbols from the four tone magnitudes of one (frequency, lag) (:216-225,243-256) followed by the caller's
+// rms gate and the deinterleaver (:751-759).  Returns the mode-2 sync value.
+__device__ float soft_symbols(const float4 *__restrict__ p, unsigned char *sym_out, float *rms_out, int symfac) {
+    float fs[NSYM];
+    float ss = 0.0f, totp = 0.0f;
+    for (int i = 0; i < NSYM; i++) {
+        float4 q = p[i];
+        totp = totp + q.x + q.y + q.z + q.w;
+        float cmet = (q.y + q.w) - (q.x + q.z);
+        if (sync_bit(i)) {
+            ss = ss + cmet;
+            fs[i] = q.w - q.y;
+        } else {
+            ss = ss - cmet;
+            fs[i] = q.z - q.x;
+        }
+    }
+    ss = ss / totp;
+    float syncmax = -1e30f;
+    if (ss > syncmax) syncmax = ss;
+    float fsum = 0.0f, f2sum = 0.0f;
+    for (int i = 0; i < NSYM; i++) {
+        fsum += fs[i] / (float)NSYM;
+        f2sum += fs[i] * fs[i] / (float)NSYM;
+    }
+    float fac = __fsqrt_rn(f2sum - fsum * fsum);
+    unsigned char tmp[NSYM];
+    float sq = 0.0f;
+    for (int i = 0; i < NSYM; i++) {
+        float v = (float)symfac * fs[i] / fac;
+        if (v > 127.0f) v = 127.0f;
+        if (v < -128.0f) v = -128.0f;
+        float w = v + 128.0f;
+        unsigned char u = (w >= 0.0f && w < 256.0f) ? (unsigned char)(int)w : (unsigned char)0;   // NaN -> 0 like cvttss2si's low byte
+        tmp[i] = u;
+        float y = (float)((double)(float)u - 128.0);
+        sq += y * y;
+    }
+    *rms_out = sqrtf(sq / (float)NSYM);
+    // deinterleave: p-th output is input at the p-th 8-bit-reversed index below 162 (wsprd_utils.c:196-213)
+    int pidx = 0;
+    for (int v = 0; pidx < NSYM; v++) {
+        int r = bitrev8(v);
+        if (r < NSYM) sym_out[pidx++] = tmp[r];
+    }
+    return syncmax;
+}
+
+// arg-max over the five frequencies, the minsync1 gate, and the jitter-0 soft symbols, which are exactly the sums
+// of the winning hypothesis (mode 2 at the same frequency and lag repeats them) -- one thread per job
+__global__ void k_pick_freq(Job *__restrict__ jobs, int njobs, const float4 *__restrict__ P1, Attempt *__restrict__ att,
+                            float minsync1, float minsync2, float minrms, int symfac) {
+    int jx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jx >= njobs) return;
+    Job &job = jobs[jx];
+    float best = -1e30f, fbest = 0.0f;
+    int bf = -1, bshift = 0;
+    for (int fi = 0; fi < NFREQ1; fi++) {
+        const float4 *p = P1 + ((size_t)jx * NFREQ1 + fi) * NSYM;
+        float ss = 0.0f, totp = 0.0f;
+        for (int i = 0; i < NSYM; i++) {
+            float4 q = p[i];
+            totp = totp + q.x + q.y + q.z + q.w;
+            float cmet = (q.y + q.w) - (q.x + q.z);
+            ss = sync_bit(i) ? ss + cmet : ss - cmet;
+        }
+        ss = ss / totp;
+        if (ss > best) {
+            best = ss;
+            bf = fi;
+            fbest = job.freq + (float)(fi - 2) * 0.1f;
+            bshift = job.shift;
+        }
+    }
+    Attempt &a = att[jx];
+    a.job = jx;
+    a.idt = 0;
+    a.gate = 0;
+    a.ok = 0;
+    a.cycles = 0;
+    a.sync2 = 0.0f;
+    job.freq = fbest;
+    job.shift = bshift;
+    job.sync1 = best;
+    job.fbest = bf;
+    job.worth = best > minsync1;
+    if (job.worth && bf >= 0) {
+        float rms;
+        float s2 = soft_symbols(P1 + ((size_t)jx * NFREQ1 + bf) * NSYM, a.sym, &rms, symfac);
+        a.sync2 = s2;
+        a.gate = (s2 > minsync2) && (rms > minrms);
+    }
+}
+
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, int njobs, float4 *P1, Attempt *att,
+                       const DecodeParams &p, cudaStream_t st) {
+    if (njobs <= 0) return;
+    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, P1, p.np, p.stride);
+    LAUNCHED();
+    k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, njobs, P1, att, p.minsync1, p.minsync2, p.minrms, p.symfac);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// K5  Fano decoder, one thread per attempt (fano.c:87-238); metric table in constant memory
+// =========================================================================================================
+__global__ void __launch_bounds__(32) k_fano(Attempt *__restrict__ att, int natt, int delta, unsigned maxcycles) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= natt) return;
+    Attempt &a = att[i];
+    if (!a.gate) return;
+    unsigned metric, cycles, maxnp;
+    unsigned char data[12];
+    for (int k = 0; k < 12; k++) data[k] = 0;
+    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, c_mettab, delta, maxcycles);
+    a.ok = (rc == 0);
+    a.cycles = cycles;
+    for (int k = 0; k < 12; k++) a.dec[k] = data[k];
+}
+
+void launch_fano(Attempt *att, int natt, const DecodeParams &p, cudaStream_t st) {
+    if (natt <= 0) return;
+    k_fano<<<(natt + 31) / 32, 32, 0, st>>>(att, natt, p.delta, p.maxcycles);
+    LAUNCHED();
+}
+
+// jobs that were worth a try but did not decode at jitter 0 go on to the jitter search (:741-766)
+__global__ void k_collect_failures(Job *__restrict__ jobs, int njobs, const Attempt *__restrict__ att0,
+                                   int *__restrict__ faillist, Counters *cnt, int quickmode) {
+    int jx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jx >= njobs) return;
+    Job &job = jobs[jx];
+    const Attempt &a = att0[jx];
+    if (a.gate) job.cycles = a.cycles;     // `cycles` keeps the last decoder call's count
+    if (a.gate && a.ok) {
+        job.decoded = 1;
+        job.idt = 0;
+        for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
+    } else if (job.worth && !quickmode) {
+        faillist[atomicAdd(&cnt->nfail, 1)] = jx;
+    }
+}
+
+void launch_collect_failures(Job *jobs, int njobs, const Attempt *att0, int *faillist, Counters *cnt, cudaStream_t st) {
+    if (njobs <= 0) return;
+    k_collect_failures<<<(njobs + 127) / 128, 128, 0, st>>>(jobs, njobs, att0, faillist, cnt, 0);
+    LAUNCHED();
+}
+
+// jitter attempts 1..42: shift + 3*(+-1..21) (:742-745), all evaluated at once; the lowest successful idt wins,
+// which is what the reference's sequential loop returns.
+__global__ void __launch_bounds__(192) k_jitter(const float *__restrict__ I, const float *__restrict__ Q,
+                                                const Job *__restrict__ jobs, const int *__restrict__ faillist,
+                                                float4 *__restrict__ P2, int np, int stride) {
+    __shared__ float4 tab[2 * SPS];
+    const Job &job = jobs[faillist[blockIdx.x]];
+    const int idt = blockIdx.y + 1, t = threadIdx.x;
+    int ii = (idt + 1) / 2;
+    if (idt % 2 == 1) ii = -ii;
+    ii = 3 * ii;
+    const bool shared_tab = (job.drift == 0.0f);
+    if (shared_tab) build_tables(job.freq, tab, t);
+    __syncthreads();
+    if (t >= NSYM) return;
+    const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
+    float fp = shared_tab ? job.freq : symbol_freq(job.freq, job.drift, t);
+    P2[((size_t)blockIdx.x * (NJIT - 1) + blockIdx.y) * NSYM + t] =
+        correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp);
+}
+__global__ void k_soft_jitter(const float4 *__restrict__ P2, Attempt *__restrict__ att1, const int *__restrict__ faillist,
+                              int natt, float minsync2, float minrms, int symfac) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= natt) return;
+    Attempt &a = att1[i];
+    a.job = faillist[i / (NJIT - 1)];
+    a.idt = i % (NJIT - 1) + 1;
+    a.ok = 0;
+    a.cycles = 0;
+    float rms;
+    float s2 = soft_symbols(P2 + (size_t)i * NSYM, a.sym, &rms, symfac);
+    a.sync2 = s2;
+    a.gate = (s2 > minsync2) && (rms > minrms);
+}
+
+void launch_jitter(const float *I, const float *Q, Job *jobs, const int *faillist, int nfail, float4 *P2, Attempt *att1,
+                   const DecodeParams &p, cudaStream_t st) {
+    if (nfail <= 0) return;
+    k_jitter<<<dim3(nfail, NJIT - 1), 192, 0, st>>>(I, Q, jobs, faillist, P2, p.np, p.stride);
+    LAUNCHED();
+    int natt = nfail * (NJIT - 1);
+    k_soft_jitter<<<(natt + 63) / 64, 64, 0, st>>>(P2, att1, faillist, natt, p.minsync2, p.minrms, p.symfac);
+    LAUNCHED();
+}
+
+__global__ void k_pick_jitter(Job *__restrict__ jobs, const int *__restrict__ faillist, int nfail,
+                              const Attempt *__restrict__ att1) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfail) return;
+    Job &job = jobs[faillist[f]];
+    for (int y = 0; y < NJIT - 1; y++) {
+        const Attempt &a = att1[(size_t)f * (NJIT - 1) + y];
+        if (a.gate) job.cycles = a.cycles;
+        if (a.gate && a.ok) {
+            job.decoded = 1;
+            job.idt = a.idt;
+            for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
+            break;
+        }
+    }
+}
+void launch_pick_jitter(Job *jobs, const int *faillist, int nfail, const Attempt *att1, cudaStream_t st) {
+    if (nfail <= 0) return;
+    k_pick_jitter<<<(nfail + 63) / 64, 64, 0, st>>>(jobs, faillist, nfail, att1);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// resolve: the per-capture, in-order tail of the candidate loop (wsprd.c:768-822): unpack the message, decide on
+// subtraction, apply the two `break`s, drop duplicates, append the spot.  One thread per capture walks the ranks
+// of the wave in order.
+// =========================================================================================================
+__global__ void k_resolve(Job *__restrict__ jobs, const int *__restrict__ jobmap, const Cand *__restrict__ cands,
+                          CapState *__restrict__ caps, Spot *__restrict__ spots, int *__restrict__ sublist,
+                          Counters *cnt, int ncap, int r0, int r1, DecodeParams p) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= ncap) return;
+    CapState &cs = caps[cap];
+    cs.sub_pending = 0;
+    if (cs.broken) return;
+    ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP};
+    for (int rank = r0; rank < r1 && rank < cs.npk; rank++) {
+        int jx = jobmap[(size_t)cap * MAXCAND + rank];
+        if (jx < 0) continue;
+        const Job &job = jobs[jx];
+        if (!(job.worth && job.decoded)) continue;
+        signed char message[12];
+        for (int i = 0; i < 11; i++) message[i] = (signed char)job.dec[i];
+        message[11] = 0;
+        char callsign[CALL_LEN], call_loc_pow[23], call[CALL_LEN], loc[7], pwr[3];
+        for (int i = 0; i < CALL_LEN; i++) callsign[i] = call[i] = 0;
+        for (int i = 0; i < 23; i++) call_loc_pow[i] = 0;
+        for (int i = 0; i < 7; i++) loc[i] = 0;
+        for (int i = 0; i < 3; i++) pwr[i] = 0;
+        int noprint = unpack_message(message, hs, call_loc_pow, call, loc, pwr, callsign);
+        if (p.subtraction && p.ipass == 0 && !noprint) {
+            if (channel_symbols(call_loc_pow, hs, cs.chan)) {
+                cs.sub_pending = 1;
+                cs.sub_f0 = job.freq;
+                cs.sub_shift = job.shift;
+                cs.sub_drift = job.drift;
+                sublist[atomicAdd(&cnt->nsub, 1)] = cap;
+            } else {
+                cs.broken = 1;
+                break;
+            }
+        }
+        if (s_eq(loc, "A000AA")) {
+            cs.broken = 1;
+            break;
+        }
+        bool dupe = false;
+        for (int i = 0; i < cs.uniques; i++)
+            if (s_eq(callsign, cs.allcalls[i]) && fabs((double)(job.freq - cs.allfreqs[i])) < 3.0) dupe = true;
+        if (dupe || cs.uniques >= MAXUNIQ) continue;
+        s_copy(cs.allcalls[cs.uniques], CALL_LEN, callsign);
+        cs.allfreqs[cs.uniques] = job.freq;
+        Spot &r = spots[(size_t)cap * MAXUNIQ + cs.uniques];
+        cs.uniques++;
+        int idt = job.idt, ii = (idt + 1) / 2;
+        if (idt % 2 == 1) ii = -ii;
+        ii = 3 * ii;
+        double dialfreq = (double)p.dialfreq / 1e6;
+        r.freq = dialfreq + (1500.0 + (double)job.freq) / 1e6;
+        r.sync = job.sync1;
+        r.snr = job.snr;
+        r.dt = (float)((double)job.shift * 1.0 / 375.0 - 2.0);
+        r.drift = job.drift;
+        r.jitter = ii;
+        r.cycles = (int)job.cycles;
+        for (int i = 0; i < 23; i++) r.message[i] = 0;
+        for (int i = 0; i < 13; i++) r.call[i] = 0;
+        for (int i = 0; i < 7; i++) r.loc[i] = 0;
+        for (int i = 0; i < 3; i++) r.pwr[i] = 0;
+        s_copy(r.message, 23, call_loc_pow);
+        s_copy(r.call, 13, call);
+        s_copy(r.loc, 7, loc);
+        s_copy(r.pwr, 3, pwr);
+    }
+}
+
+void launch_resolve(Job *jobs, const int *jobmap, const Cand *cands, CapState *caps, Spot *spots, int *sublist,
+                    Counters *cnt, int ncap, int r0, int r1, const DecodeParams &p, cudaStream_t st) {
+    if (ncap <= 0) return;
+    k_resolve<<<(ncap + 31) / 32, 32, 0, st>>>(jobs, jobmap, cands, caps, spots, sublist, cnt, ncap, r0, r1, p);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// K6  subtract_signal2 (wsprd.c:316-413)
+//   (a) the reference phase is a float running sum over all 41 472 samples; one thread per job replays the
+//       additions and records the phase at every symbol start;
+//   (b) per symbol: replay 256 additions, cos/sin (glibc-faithful), s(t)*conj(r(t)) into a zero-padded buffer;
+//   (c) 360-tap low-pass (each output a sequential 360-term sum, four consecutive outputs per thread with a
+//       sliding register window), edge renormalisation, subtraction in place.
+// =========================================================================================================
+__device__ __forceinline__ float sub_dphi(float f0, float drift, int i, unsigned char sym) {   // :341-343
+    float cs = (float)sym;
+    return (float)(twopidt() * ((double)f0 +
+                                ((double)drift / 2.0) * ((double)(float)i - (double)(float)NSYM / 2.0) / ((double)(float)NSYM / 2.0) +
+                                ((double)cs - 1.5) * 375.0 / 256.0));
+}
+
+__global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__restrict__ sublist, int nsub,
+                            float *__restrict__ phi0) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsub) return;
+    const CapState &cs = caps[sublist[s]];
+    float phi = 0.0f;
+    for (int i = 0; i < NSYM; i++) {
+        phi0[(size_t)s * NSYM + i] = phi;
+        float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
+        for (int j = 0; j < SPS; j++) phi = phi + dphi;
+    }
+}
+
+__global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, const float *__restrict__ Q,
+                                                 const CapState *__restrict__ caps, const int *__restrict__ sublist,
+                                                 const float *__restrict__ phi0, float2 *__restrict__ ref,
+                                                 float2 *__restrict__ cprod, int np, int stride) {
+    __shared__ float s_phi[SPS];
+    const int s = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
+    const int cap = sublist[s];
+    const CapState &cs = caps[cap];
+    if (i >= NSYM) {                    // extra CTAs zero the pads of the product buffer
+        float2 *c = cprod + (size_t)s * CPAD;
+        int z = (i - NSYM) * SPS + j;   // 0 .. 2*256-1 ; we need [0,360) and [360+NSIG, CPAD)
+        if (z < NFILT) c[z] = make_float2(0.0f, 0.0f);
+        int tailn = CPAD - (NFILT + NSIG);
+        if (z < tailn) c[NFILT + NSIG + z] = make_float2(0.0f, 0.0f);
+        return;
+    }
+    if (j == 0) {
+        float phi = phi0[(size_t)s * NSYM + i];
+        float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
+        for (int q = 0; q < SPS; q++) {
+            s_phi[q] = phi;
+            phi = phi + dphi;
+        }
+    }
+    __syncthreads();
+    const float phi = s_phi[j];
+    const float rc = glibc_cosf(phi), rs = glibc_sinf(phi);
+    const int ii = i * SPS + j, k = cs.sub_shift + ii;
+    float2 c = make_float2(0.0f, 0.0f);
+    if (k > 0 && k < np) {               // :375-381
+        float x = I[(size_t)cap * stride + k], y = Q[(size_t)cap * stride + k];
+        c.x = x * rc + y * rs;
+        c.y = y * rc - x * rs;
+    }
+    ref[(size_t)s * NSIG + ii] = make_float2(rc, rs);
+    cprod[(size_t)s * CPAD + NFILT + ii] = c;
+}
+
+constexpr int LPF_THREADS = 256;
+constexpr int LPF_R = 4;                                     // consecutive outputs per thread
+constexpr int LPF_TILE = LPF_THREADS * LPF_R;                // 1024 outputs per CTA
+constexpr int LPF_SPAN = LPF_TILE + NFILT;                   // inputs per tile (1384, multiple of 4)
+constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
+
+__global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, float *__restrict__ Q,
+                                                         const CapState *__restrict__ caps, const int *__restrict__ sublist,
+                                                         const float2 *__restrict__ ref, const float2 *__restrict__ cprod,
+                                                         int np, int stride) {
+    __shared__ float2 sc[LPF_R * LPF_PITCH];
+    const int s = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
+    const int cap = sublist[s];
+    const CapState &cs = caps[cap];
+    const int i0 = tile * LPF_TILE;                          // first output (signal sample index) of the tile
+    // output i needs cprod[i + NFILT/2 + tap], tap = 0..359 (cf index i+360, window starts 180 earlier)
+    const float2 *src = cprod + (size_t)s * CPAD + i0 + NFILT / 2;
+    for (int m = t; m < LPF_SPAN; m += LPF_THREADS) {
+        int g = i0 + NFILT / 2 + m;
+        sc[(m % LPF_R) * LPF_PITCH + m / LPF_R] = (g < CPAD) ? src[m] : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+    float ai[LPF_R], aq[LPF_R];
+    float2 w[LPF_R];                                         // sliding window: inputs 4t+tap .. 4t+tap+3
+#pragma unroll
+    for (int r = 0; r < LPF_R; r++) {
+        ai[r] = aq[r] = 0.0f;
+        w[r] = sc[r * LPF_PITCH + t];
+    }
+    for (int tap = 0; tap < NFILT; tap += LPF_R) {
+#pragma unroll
+        for (int u = 0; u < LPF_R; u++) {
+            const float wt = c_lpf_w[tap + u];
+            // at tap+u the window holds inputs (4t + tap+u + r); rotate by u
+#pragma unroll
+            for (int r = 0; r < LPF_R; r++) {
+                float2 v = w[(u + r) % LPF_R];
+                ai[r] = ai[r] + wt * v.x;                      // :388-389
+                aq[r] = aq[r] + wt * v.y;
+            }
+            // slot u now leaves the window; refill it with input 4t + tap+u + 4
+            int m = LPF_R * t + tap + u + LPF_R;
+            w[u] = sc[(m % LPF_R) * LPF_PITCH + m / LPF_R];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < LPF_R; r++) {                         // :397-410
+        int i = i0 + LPF_R * t + r;
+        if (i >= NSIG) continue;
+        float norm;
+        if (i < NFILT / 2) norm = c_lpf_psum[NFILT / 2 + i];
+        else if (i > NSIG - 1 - NFILT / 2) norm = c_lpf_psum[NFILT / 2 + NSIG - 1 - i];
+        else norm = 1.0f;
+        int k = cs.sub_shift + i;
+        if (k > 0 && k < np) {
+            float2 rr = ref[(size_t)s * NSIG + i];
+            size_t g = (size_t)cap * stride + k;
+            I[g] = I[g] - (ai[r] * rr.x - aq[r] * rr.y) / norm;
+            Q[g] = Q[g] - (ai[r] * rr.y + aq[r] * rr.x) / norm;
+        }
+    }
+}
+
+void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublist, int nsub, float *phi0, float2 *ref,
+                     float2 *cprod, const DecodeParams &p, cudaStream_t st) {
+    if (nsub <= 0) return;
+    k_sub_phase<<<(nsub + 31) / 32, 32, 0, st>>>(caps, sublist, nsub, phi0);
+    LAUNCHED();
+    k_sub_ref<<<dim3(nsub, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, phi0, ref, cprod, p.np, p.stride);
+    LAUNCHED();
+    k_sub_lpf<<<dim3(nsub, (NSIG + LPF_TILE - 1) / LPF_TILE), LPF_THREADS, 0, st>>>(I, Q, caps, sublist, ref, cprod, p.np,
+                                                                                    p.stride);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// bookkeeping kernels
+// =========================================================================================================
+__global__ void k_reset_caps(CapState *caps, int ncap) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= ncap) return;
+    CapState &cs = caps[cap];
+    cs.npk = 0;
+    cs.uniques = 0;
+    cs.broken = 0;
+    cs.nhash = 0;
+    cs.sub_pending = 0;
+}
+void launch_reset_caps(CapState *caps, int ncap, cudaStream_t st) {
+    if (ncap <= 0) return;
+    k_reset_caps<<<(ncap + 127) / 128, 128, 0, st>>>(caps, ncap);
+    LAUNCHED();
+}
+
+// final stable sort by SNR, descending (wsprd.c:827) and the spot count
+__global__ void k_finish(CapState *__restrict__ caps, Spot *__restrict__ spots, int *__restrict__ nres, int ncap) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= ncap) return;
+    Spot *r = spots + (size_t)cap * MAXUNIQ;
+    int n = caps[cap].uniques;
+    for (int i = 1; i < n; i++) {
+        Spot x = r[i];
+        int j = i;
+        while (j > 0 && r[j - 1].snr < x.snr) {
+            r[j] = r[j - 1];
+            j--;
+        }
+        r[j] = x;
+    }
+    nres[cap] = n;
+}
+void launch_finish(CapState *caps, Spot *spots, int *nres, int ncap, cudaStream_t st) {
+    if (ncap <= 0) return;
+    k_finish<<<(ncap + 31) / 32, 32, 0, st>>>(caps, spots, nres, ncap);
+    LAUNCHED();
+}
+
+// peak normalisation of the hand-off (rtlsdr_wsprd.c:291-305): scale = (float)(0.5 / max(|I|,|Q|, 1e-24))
+__global__ void __launch_bounds__(256) k_normalise(float *__restrict__ I, float *__restrict__ Q, int n, int stride) {
+    __shared__ float red[256];
+    const int cap = blockIdx.x, t = threadIdx.x;
+    float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
+    float m = 1e-24f;
+    for (int i = t; i < n; i += 256) {
+        float a = fabsf(ip[i]), b = fabsf(qp[i]);
+        if (a > m) m = a;
+        if (b > m) m = b;
+    }
+    red[t] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s && red[t + s] > red[t]) red[t] = red[t + s];
+        __syncthreads();
+    }
+    const float scale = (float)(0.5 / (double)red[0]);
+    for (int i = t; i < n; i += 256) {
+        ip[i] *= scale;
+        qp[i] *= scale;
+    }
+}
+void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStream_t st) {
+    if (ncap <= 0 || n <= 0) return;
+    k_normalise<<<ncap, 256, 0, st>>>(I, Q, n, stride);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// generic sync_and_demodulate correlation grid for the reference-ABI wrapper: P[(f*nlags + l)*162 + sym]
+// =========================================================================================================
+__global__ void __launch_bounds__(192) k_sync_generic(const float *__restrict__ I, const float *__restrict__ Q, int np,
+                                                      float freq, int ifmin, float fstep, int lagmin, int lagstep,
+                                                      float drift, float4 *__restrict__ P) {
+    __shared__ float4 tab[2 * SPS];
+    const int l = blockIdx.x, fi = blockIdx.y, t = threadIdx.x;
+    const float f0 = freq + (float)(ifmin + fi) * fstep;
+    const bool shared_tab = (drift == 0.0f);
+    if (shared_tab) build_tables(f0, tab, t);
+    __syncthreads();
+    if (t >= NSYM) return;
+    float fp = shared_tab ? f0 : symbol_freq(f0, drift, t);
+    P[((size_t)fi * gridDim.x + l) * NSYM + t] = correlate_symbol(I, Q, np, lagmin + l * lagstep + t * SPS, shared_tab, tab, fp);
+}
+void launch_sync_generic(const float *I, const float *Q, int np, float freq, int ifmin, int ifmax, float fstep, int lagmin,
+                         int lagmax, int lagstep, float drift, float4 *P, cudaStream_t st) {
+    int nf = ifmax - ifmin + 1, nl = (lagmax - lagmin) / lagstep + 1;
+    if (nf <= 0 || nl <= 0) return;
+    k_sync_generic<<<dim3(nl, nf), 192, 0, st>>>(I, Q, np, freq, ifmin, fstep, lagmin, lagstep, drift, P);
+    LAUNCHED();
+}
+
+}  // namespace wspr

@@ -1,0 +1,152 @@
+// Device data structures and kernel declarations of the batched WSPR decode path.
+// (The kernels live in wspr_kernels.cu, the host-side wave scheduler in wspr_decode.cu.)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wspr_codec.cuh"
+
+namespace wspr {
+
+constexpr int NFFT = 512;
+constexpr int HOP = 128;
+constexpr int MAXCAND = 200;     // MAX_CANDIDATES, wsprd/wsprd.h:40
+constexpr int MAXUNIQ = 100;     // MAX_UNIQUES,    wsprd/wsprd.h:41
+constexpr int NSMOOTH = 411;     // smoothed-spectrum bins, wsprd.c:566
+constexpr int MAXLAGS = 33;      // (128+128)/8 + 1 lags of the mode-0 search, wsprd.c:713-715
+constexpr int NFREQ1 = 5;        // mode-1 frequency hypotheses, wsprd.c:722-724
+constexpr int NJIT = 43;         // jitter attempts 0..42, wsprd.c:741
+constexpr int NFILT = 360;       // subtract_signal2 low-pass length, wsprd.c:325
+constexpr int NSIG = NSYM * SPS; // 41472 samples of one transmission
+constexpr int CPAD = 42240;      // padded length of the s*conj(r) product (NSIG + 2*NFILT, rounded up)
+constexpr int HASH_CAP = 224;    // per-capture callsign-hash entries kept on the device
+
+// struct cand, wsprd/wsprd.h:54-60
+struct Cand {
+    float freq, snr;
+    int shift;
+    float drift, sync;
+};
+
+// struct decoder_results, wsprd/wsprd.h:62-74 (80 bytes; layout checked with static_assert in wspr_decode.cu)
+struct Spot {
+    double freq;
+    float sync, snr, dt, drift;
+    int jitter;
+    char message[23];
+    char call[13];
+    char loc[7];
+    char pwr[3];
+    int cycles;
+};
+
+// decode thresholds and options (wsprd.c:424-433, wsprd.h:44-52)
+struct DecodeParams {
+    int np;             // samples per capture (45000)
+    int stride;         // floats between captures in the I/Q planes
+    int blocks;         // spectrogram columns (347)
+    int dialfreq;       // options.freq
+    int quickmode, subtraction;
+    int ipass;
+    int maxdrift;       // 4, or 0 in a third pass
+    float minsync1, minsync2, minrms;
+    int symfac, delta;
+    unsigned maxcycles;
+    int lagstep;        // 8, or 16 in quick mode
+    int nlags;          // 33 / 17
+};
+
+// one candidate being refined in the current wave
+struct Job {
+    int cap, rank;
+    float freq, drift;
+    int shift;
+    float sync1;        // sync after the frequency search (what the spot reports)
+    float snr;
+    int worth;          // sync1 > minsync1
+    int fbest;          // winning mode-1 hypothesis (its sums are the jitter-0 soft symbols)
+    int decoded;        // a Fano attempt succeeded
+    int idt;            // winning jitter attempt
+    unsigned cycles;
+    unsigned char dec[12];
+};
+
+// one soft-decision attempt (candidate x jitter)
+struct Attempt {
+    int job;
+    int idt;
+    int gate;           // sync and rms gates passed -> run the Fano decoder
+    int ok;             // decoder result: 1 = decoded
+    unsigned cycles;
+    float sync2;
+    unsigned char dec[12];
+    unsigned char sym[NSYM + 2];   // deinterleaved soft symbols
+};
+
+// per-capture bookkeeping across candidates and passes (everything wspr_decode keeps on its stack)
+struct CapState {
+    int npk;            // candidates of the current pass
+    int uniques;
+    int broken;         // the reference hit one of its `break`s in this pass
+    int nhash;
+    int sub_pending;    // a subtraction has been scheduled by the resolve step
+    float sub_f0, sub_drift;
+    int sub_shift;
+    float allfreqs[MAXUNIQ];
+    char allcalls[MAXUNIQ][CALL_LEN];
+    HashEntry hash[HASH_CAP];
+    unsigned char chan[NSYM + 2];
+};
+
+struct Counters {
+    int njobs, nfail, nsub, nattempt, maxnpk, totnpk;
+    int pad[2];
+};
+
+// constant tables uploaded once per process (host libm values where the reference computes them with libm)
+struct HostTables {
+    float window[NFFT];       // sinf(0.006147931*i), wsprd.c:510-513
+    float lpf_w[NFILT];       // normalised half-sine taps, wsprd.c:359-365
+    float lpf_psum[NFILT];    // running sums, wsprd.c:366-368
+    float min_snr;            // powf(10, -0.8), wsprd.c:590
+    float floor_snr;          // (float)(0.1*min_snr), wsprd.c:595
+};
+void upload_tables(const HostTables &t);
+
+// ---- launchers (all asynchronous on `st`) ----
+void launch_spectrogram(const float *I, const float *Q, float *psT, int ncap, const DecodeParams &p, cudaStream_t st);
+void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, Counters *cnt, int ncap,
+                       const DecodeParams &p, cudaStream_t st);
+void launch_coarse(const float *psT, Cand *cands, const CapState *caps, int ncap, int maxnpk, const DecodeParams &p,
+                   cudaStream_t st);
+void launch_make_jobs(const Cand *cands, const CapState *caps, Job *jobs, int *jobmap, Counters *cnt, int ncap, int r0,
+                      int r1, int jobcap, cudaStream_t st);
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, int njobs, float4 *P0, const DecodeParams &p,
+                      cudaStream_t st);
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, int njobs, float4 *P1, Attempt *att,
+                       const DecodeParams &p, cudaStream_t st);
+void launch_fano(Attempt *att, int natt, const DecodeParams &p, cudaStream_t st);
+void launch_collect_failures(Job *jobs, int njobs, const Attempt *att0, int *faillist, Counters *cnt, cudaStream_t st);
+void launch_jitter(const float *I, const float *Q, Job *jobs, const int *faillist, int nfail, float4 *P2, Attempt *att1,
+                   const DecodeParams &p, cudaStream_t st);
+void launch_pick_jitter(Job *jobs, const int *faillist, int nfail, const Attempt *att1, cudaStream_t st);
+void launch_resolve(Job *jobs, const int *jobmap, const Cand *cands, CapState *caps, Spot *spots, int *sublist,
+                    Counters *cnt, int ncap, int r0, int r1, const DecodeParams &p, cudaStream_t st);
+void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublist, int nsub, float *phi0, float2 *ref,
+                     float2 *cprod, const DecodeParams &p, cudaStream_t st);
+void launch_finish(CapState *caps, Spot *spots, int *nres, int ncap, cudaStream_t st);
+void launch_reset_caps(CapState *caps, int ncap, cudaStream_t st);
+void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStream_t st);
+
+// stand-alone single-call forms used by the reference-ABI wrappers (sync_and_demodulate / subtract_signal2)
+void launch_sync_generic(const float *I, const float *Q, int np, float freq, int ifmin, int ifmax, float fstep, int lagmin,
+                         int lagmax, int lagstep, float drift, float4 *P, cudaStream_t st);
+
+// front end (rtlsdr_wsprd.c:126-244)
+void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint32_t *blocksums,
+                     float *I, float *Q, int out_stride, int max_out, cudaStream_t st);
+int decimate_outputs(size_t n_iq);
+
+unsigned long long kernel_launch_count();
+
+}  // namespace wspr
