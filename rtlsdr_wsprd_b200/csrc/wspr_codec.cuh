@@ -17,7 +17,7 @@
 
 #ifdef __CUDACC__
 #define WHD __host__ __device__ __forceinline__
-#define WHD_NOINLINE __host__ __device__
+#define WHD_NOINLINE inline __host__ __device__
 #else
 #define WHD inline
 #define WHD_NOINLINE inline

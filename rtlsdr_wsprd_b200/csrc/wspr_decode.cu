@@ -268,9 +268,6 @@ static int run_wave(wspr_ctx *c, const DecodeParams &p, int r0, int r1) {
     }
     launch_sync_freqs(c->I, c->Q, c->jobs, njobs, c->P1, c->att0, p, c->st);
     launch_fano(c->att0, njobs, p, c->st);
-    {
-        extern void launch_collect_failures_q(Job *, int, const Attempt *, int *, Counters *, int, cudaStream_t);
-    }
     launch_collect_failures(c->jobs, njobs, c->att0, c->faillist, c->cnt, c->st);
     if (!p.quickmode) {
         if (read_counters(c)) return WSPR_ERR_CUDA;
@@ -452,6 +449,7 @@ static wspr_ctx *single_ctx(int samples) {
 extern "C" int wspr_decode(float *idat, float *qdat, int samples, decoder_options options, decoder_results *decodes,
                            int *n_results) {
     if (n_results) *n_results = 0;
+    g_err.clear();
     wspr_ctx *c = single_ctx(samples);
     std::vector<decoder_results> tmp(MAXUNIQ);
     int n = 0;

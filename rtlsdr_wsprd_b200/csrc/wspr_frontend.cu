@@ -1,0 +1,355 @@
+// K0  front end: raw RTL-SDR stream (interleaved u8 I/Q at 2.4 Msps) -> 375 sps float I/Q, bit-identical to
+// rtlsdr_callback (rtlsdr_wsprd.c:126-244): fs/4 mixer (:171-182), two int32 integrators (:190-195), decimation by
+// 6401 (:198-202), two delay-2 combs (:204-218), 33-tap float FIR evaluated in tap order (:221-234).
+//
+// The reference runs the integrators sample by sample.  They are linear over Z/2^32, so the value of the second
+// integrator at the decimation instant of block m (a block = 6401 consecutive samples) is
+//       v[m] = (m+1)*6401 * sum_{b<=m} S0[b]  -  sum_{b<=m} (b*6401*S0[b] + S1[b])        (mod 2^32)
+// with per-block moments S0[b] = sum x[t], S1[b] = sum t*x[t] (t = index inside the block, x = mixer output).
+//   k_block_moments : the HBM-bound pass -- one warp per block, 16-byte loads, byte sums with dp4a
+//   k_comb_fir      : per stream, a wrapping prefix scan of the moments, the two combs and the FIR
+// Compiled with -fmad=false (the FIR multiplies and adds round separately, like the reference's x86-64 build).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/wspr_b200.h"
+#include "wspr_kernels.cuh"
+
+namespace wspr {
+
+extern unsigned long long g_frontend_launches;
+unsigned long long g_frontend_launches = 0;
+
+constexpr int DECIM = 6401;                 // DOWNSAMPLING + 1, see the header comment
+constexpr int BLOCK_BYTES = 2 * DECIM;      // 12802
+constexpr int FIR_TAPS = 32;
+
+// The 33 FIR coefficients are data of the reference (rtlsdr_wsprd.c:142-152), symmetric; the 17 distinct values:
+__constant__ float c_fir[33];
+static const float h_fir_half[17] = {-0.0027772683, -0.0005058826, 0.0049745750,  -0.0034059318, -0.0077557814, 0.0139375423,
+                                     0.0039896935,  -0.0299394142, 0.0162250643,  0.0405130860,  -0.0580746013, -0.0272104968,
+                                     0.1183705475,  -0.0306029022, -0.2011241667, 0.1615898423,  0.5000000000};
+
+int decimate_outputs(size_t n_iq) { return (int)std::min<size_t>(n_iq / DECIM, 1u << 30); }
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {   // sum of (unsigned byte of a) * (signed byte of b) + c
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {        // read-once data: bypass L1 allocation
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// Mixer weights.  A 16-byte vector holds samples n = 8V .. 8V+7 as bytes (I0 Q0 I1 Q1 | I2 Q2 I3 Q3 | ...), and
+// 8V = 0 mod 4, so word 0/2 holds mixer phases 0,1 and word 1/3 phases 2,3:
+//   phase 0: (I,Q) ; 1: (-Q, I) ; 2: (-I,-Q) ; 3: (Q,-I)                       (rtlsdr_wsprd.c:171-182)
+// Bytes are used offset-binary (u = s + 128); the -128*sum(weights) term vanishes because every weight vector
+// below sums to zero over a whole vector only for the cross terms -- it is therefore removed explicitly: each
+// accumulated sum is corrected by 128 * (sum of the weights applied), which is tracked in closed form (all
+// weights of one channel over one vector cancel: +1 -1 -1 +1), except that masked (out-of-block) bytes are
+// replaced by 128 so that they contribute s = 0.
+// The reference negates in int8, so -(-128) stays -128: a negated byte with u == 0 contributes 256 less than
+// the linear sum.  Vectors containing a zero byte take a per-byte correction path.
+#define PACK4(a, b, c, d) ((int)(((unsigned)(a)&255u) | (((unsigned)(b)&255u) << 8) | (((unsigned)(c)&255u) << 16) | (((unsigned)(d)&255u) << 24)))
+
+struct Moments {
+    int s0i, s0q, s1i, s1q;
+};
+
+// accumulate one 16-byte vector whose first sample has in-block index t0 (may be negative at the leading edge;
+// bytes outside the block are already forced to 128)
+__device__ __forceinline__ void accumulate_vector(Moments &m, const uint4 v, int t0) {
+    // zeroth moment: sum of mixer outputs of the 8 samples
+    int ai = dp4a_us(v.x, PACK4(1, 0, 0, -1), 0);
+    ai = dp4a_us(v.y, PACK4(-1, 0, 0, 1), ai);
+    ai = dp4a_us(v.z, PACK4(1, 0, 0, -1), ai);
+    ai = dp4a_us(v.w, PACK4(-1, 0, 0, 1), ai);
+    int aq = dp4a_us(v.x, PACK4(0, 1, 1, 0), 0);
+    aq = dp4a_us(v.y, PACK4(0, -1, -1, 0), aq);
+    aq = dp4a_us(v.z, PACK4(0, 1, 1, 0), aq);
+    aq = dp4a_us(v.w, PACK4(0, -1, -1, 0), aq);
+    // first moment about the vector's first sample: offsets 0..7
+    int bi = dp4a_us(v.x, PACK4(0, 0, 0, -1), 0);
+    bi = dp4a_us(v.y, PACK4(-2, 0, 0, 3), bi);
+    bi = dp4a_us(v.z, PACK4(4, 0, 0, -5), bi);
+    bi = dp4a_us(v.w, PACK4(-6, 0, 0, 7), bi);
+    int bq = dp4a_us(v.x, PACK4(0, 0, 1, 0), 0);
+    bq = dp4a_us(v.y, PACK4(0, -2, -3, 0), bq);
+    bq = dp4a_us(v.z, PACK4(0, 4, 5, 0), bq);
+    bq = dp4a_us(v.w, PACK4(0, -6, -7, 0), bq);
+    // remove the +128 offset of the bytes: 128 * (sum of weights).  Zeroth-moment weights cancel (1-1-1+1 = 0 for I,
+    // 1+1-1-1-... = 0 for Q); first-moment weights sum to -1-2+3+4-5-6+7 = 0 for I and 0+1-2-3+4+5-6-7 = -8 for Q.
+    bq += 128 * 8;
+    m.s0i += ai;
+    m.s0q += aq;
+    m.s1i += t0 * ai + bi;
+    m.s1q += t0 * aq + bq;
+    // int8 negation wrap for u == 0 (s == -128) at the negated positions: word x byte 3 (I of phase 1),
+    // word y bytes 0,1 (I,Q of phase 2) and byte 2 (Q of phase 3); same for z/w.
+    const unsigned z = ((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) | ((v.z - 0x01010101u) & ~v.z) |
+                       ((v.w - 0x01010101u) & ~v.w);
+    if (z & 0x80808080u) {
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int tk = t0 + 2 * k;        // in-block index of the word's first sample
+            if (k & 1) {
+                if ((w[k] & 0x000000ffu) == 0) { m.s0i -= 256; m.s1i -= 256 * tk; }            // -I, phase 2
+                if ((w[k] & 0x0000ff00u) == 0) { m.s0q -= 256; m.s1q -= 256 * tk; }            // -Q, phase 2
+                if ((w[k] & 0x00ff0000u) == 0) { m.s0q -= 256; m.s1q -= 256 * (tk + 1); }      // Q = -I, phase 3
+            } else {
+                if ((w[k] & 0xff000000u) == 0) { m.s0i -= 256; m.s1i -= 256 * (tk + 1); }      // I = -Q, phase 1
+            }
+        }
+    }
+}
+
+// force the bytes of a vector that lie outside [lo, hi) (byte offsets relative to the vector start) to 128
+__device__ __forceinline__ uint4 mask_vector(uint4 v, int lo, int hi) {
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned keep = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int pos = 4 * k + b;
+            if (pos >= lo && pos < hi) keep |= 0xffu << (8 * b);
+        }
+        w[k] = (w[k] & keep) | (0x80808080u & ~keep);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+constexpr int MOM_WARPS = 8;
+constexpr int MOM_UNROLL = 5;
+
+// one warp per 6401-sample block.  raw must be 16-byte aligned per stream.
+__global__ void __launch_bounds__(MOM_WARPS * 32) k_block_moments(const uint8_t *__restrict__ raw, size_t stream_stride,
+                                                                  int nblk, uint4 *__restrict__ moments) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * MOM_WARPS + warp, stream = blockIdx.y;
+    if (b >= nblk) return;
+    const uint8_t *base = raw + (size_t)stream * stream_stride;
+    const long long byte0 = (long long)b * BLOCK_BYTES, byte1 = byte0 + BLOCK_BYTES;
+    const long long v0 = byte0 >> 4, v1 = (byte1 + 15) >> 4;        // vectors [v0, v1) cover the block
+    const int nvec = (int)(v1 - v0);                                 // 801 or 802
+    const uint4 *vp = reinterpret_cast<const uint4 *>(base) + v0;
+    const int lead = (int)(byte0 - (v0 << 4));                       // bytes of vector 0 before the block
+    const int tail = (int)((v1 << 4) - byte1);                       // bytes of the last vector after the block
+    const int tfirst = -(lead >> 1);                                 // in-block index of vector 0's first sample
+    Moments m = {0, 0, 0, 0};
+    // interior vectors 1 .. nvec-2 need no masking
+    int i = 1 + lane;
+    for (; i + 32 * (MOM_UNROLL - 1) < nvec - 1; i += 32 * MOM_UNROLL) {
+        uint4 v[MOM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MOM_UNROLL; u++) v[u] = ld_stream(vp + i + 32 * u);
+#pragma unroll
+        for (int u = 0; u < MOM_UNROLL; u++) accumulate_vector(m, v[u], tfirst + 8 * (i + 32 * u));
+    }
+    for (; i < nvec - 1; i += 32) accumulate_vector(m, ld_stream(vp + i), tfirst + 8 * i);
+    if (lane == 0) accumulate_vector(m, mask_vector(ld_stream(vp), lead, 16), tfirst);
+    if (lane == 1) accumulate_vector(m, mask_vector(ld_stream(vp + nvec - 1), 0, 16 - tail), tfirst + 8 * (nvec - 1));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        m.s0i += __shfl_xor_sync(0xffffffffu, m.s0i, s);
+        m.s0q += __shfl_xor_sync(0xffffffffu, m.s0q, s);
+        m.s1i += __shfl_xor_sync(0xffffffffu, m.s1i, s);
+        m.s1q += __shfl_xor_sync(0xffffffffu, m.s1q, s);
+    }
+    if (lane == 0) moments[(size_t)stream * nblk + b] = make_uint4((unsigned)m.s0i, (unsigned)m.s0q, (unsigned)m.s1i, (unsigned)m.s1q);
+}
+
+// per stream: wrapping inclusive scans P = sum S0, W = sum (b*6401*S0 + S1); v = (b+1)*6401*P - W; combs; FIR.
+// One CTA per stream; every thread owns a contiguous run of blocks.  `vals` is a [stream][nblk] uint2 scratch.
+constexpr int CF_THREADS = 1024;
+__global__ void __launch_bounds__(CF_THREADS) k_comb_fir(const uint4 *__restrict__ moments, uint2 *__restrict__ vals, int nblk,
+                                                         float *__restrict__ I, float *__restrict__ Q, int out_stride,
+                                                         int max_out) {
+    __shared__ uint4 part[CF_THREADS];
+    const int stream = blockIdx.x, t = threadIdx.x;
+    const uint4 *mom = moments + (size_t)stream * nblk;
+    uint2 *val = vals + (size_t)stream * nblk;
+    const int per = (nblk + CF_THREADS - 1) / CF_THREADS;
+    const int b0 = min(t * per, nblk), b1 = min(b0 + per, nblk);
+    uint4 acc = make_uint4(0, 0, 0, 0);      // (P_i, P_q, W_i, W_q) of this thread's run
+    for (int b = b0; b < b1; b++) {
+        uint4 s = mom[b];
+        const unsigned off = (unsigned)b * (unsigned)DECIM;
+        acc.x += s.x;
+        acc.y += s.y;
+        acc.z += off * s.x + s.z;
+        acc.w += off * s.y + s.w;
+    }
+    part[t] = acc;
+    __syncthreads();
+    for (int d = 1; d < CF_THREADS; d <<= 1) {     // Hillis-Steele inclusive scan (wrapping adds are associative)
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (t >= d) o = part[t - d];
+        __syncthreads();
+        if (t >= d) {
+            uint4 p = part[t];
+            part[t] = make_uint4(p.x + o.x, p.y + o.y, p.z + o.z, p.w + o.w);
+        }
+        __syncthreads();
+    }
+    uint4 run = (t == 0) ? make_uint4(0, 0, 0, 0) : part[t - 1];
+    for (int b = b0; b < b1; b++) {
+        uint4 s = mom[b];
+        const unsigned off = (unsigned)b * (unsigned)DECIM;
+        run.x += s.x;
+        run.y += s.y;
+        run.z += off * s.x + s.z;
+        run.w += off * s.y + s.w;
+        const unsigned n1 = (unsigned)(b + 1) * (unsigned)DECIM;
+        val[b] = make_uint2(n1 * run.x - run.z, n1 * run.y - run.w);
+    }
+    __syncthreads();                               // val[] written by this CTA only; make it visible CTA-wide
+    const int nout = min(nblk, max_out);
+    for (int m = t; m < max_out; m += CF_THREADS) {
+        float oi = 0.0f, oq = 0.0f;
+        if (m < nout) {
+            // comb outputs f[k] = v[k] - 2 v[k-2] + v[k-4] (zero history) for k = m-32 .. m, then the FIR in tap order
+            float si = 0.0f, sq = 0.0f;
+#pragma unroll 1
+            for (int j = 0; j <= FIR_TAPS; j++) {
+                const int k = m - FIR_TAPS + j;
+                float fi = 0.0f, fq = 0.0f;
+                if (k >= 0) {
+                    uint2 a = val[k];
+                    uint2 c = (k >= 2) ? val[k - 2] : make_uint2(0, 0);
+                    uint2 e = (k >= 4) ? val[k - 4] : make_uint2(0, 0);
+                    fi = (float)(int)(a.x - 2u * c.x + e.x);
+                    fq = (float)(int)(a.y - 2u * c.y + e.y);
+                }
+                const float z = c_fir[j];
+                si = si + fi * z;
+                sq = sq + fq * z;
+            }
+            oi = si;
+            oq = sq;
+        }
+        I[(size_t)stream * out_stride + m] = oi;
+        Q[(size_t)stream * out_stride + m] = oq;
+    }
+}
+
+static bool g_fir_uploaded[64] = {false};
+static cudaError_t upload_fir() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_fir_uploaded[dev]) return cudaSuccess;
+    float z[33];
+    for (int j = 0; j < 33; j++) z[j] = h_fir_half[j <= 16 ? j : 32 - j];
+    cudaError_t e = cudaMemcpyToSymbol(c_fir, z, sizeof z);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) g_fir_uploaded[dev] = true;
+    return e;
+}
+
+// moments: [nstreams][nblk] uint4, vals: [nstreams][nblk] uint2 (scratch, device)
+void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, uint2 *vals,
+                     float *I, float *Q, int out_stride, int max_out, cudaStream_t st) {
+    const int nblk = decimate_outputs(n_iq);
+    if (nstreams <= 0 || max_out <= 0) return;
+    upload_fir();
+    if (nblk > 0) {
+        k_block_moments<<<dim3((nblk + MOM_WARPS - 1) / MOM_WARPS, nstreams), MOM_WARPS * 32, 0, st>>>(raw, stream_stride_bytes,
+                                                                                                      nblk, (uint4 *)moments);
+        g_frontend_launches++;
+    }
+    k_comb_fir<<<nstreams, CF_THREADS, 0, st>>>(moments, vals, nblk, I, Q, out_stride, max_out);
+    g_frontend_launches++;
+}
+
+}  // namespace wspr
+
+using namespace wspr;
+
+static thread_local std::string g_fe_err;
+extern "C" const char *wspr_frontend_last_error(void) { return g_fe_err.c_str(); }
+static int fe_fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+    g_fe_err = what;
+    if (e != cudaSuccess) {
+        g_fe_err += ": ";
+        g_fe_err += cudaGetErrorString(e);
+    }
+    return code;
+}
+#define FCK(call)                                                        \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) { rc = fe_fail(WSPR_ERR_CUDA, #call, e_); goto done; } \
+    } while (0)
+
+static float g_fe_last_ms = 0.0f;
+extern "C" float wspr_decimate_last_ms(void) { return g_fe_last_ms; }
+
+extern "C" int wspr_decimate_device(const uint8_t *d_raw, int nstreams, size_t n_iq, size_t stream_stride_bytes, float *dI,
+                                    float *dQ, int out_stride, int max_out, int device) {
+    if (nstreams < 0 || !d_raw || !dI || !dQ || max_out < 0 || out_stride < max_out) return fe_fail(WSPR_ERR_ARG, "wspr_decimate_device: bad arguments");
+    if (((uintptr_t)d_raw & 15) || (stream_stride_bytes & 15) || stream_stride_bytes < 2 * n_iq)
+        return fe_fail(WSPR_ERR_ARG, "wspr_decimate_device: raw streams must be 16-byte aligned and strided");
+    if (nstreams == 0 || max_out == 0) return 0;
+    int rc = WSPR_OK;
+    const int nblk = decimate_outputs(n_iq);
+    uint4 *mom = nullptr;
+    uint2 *vals = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (device >= 0) FCK(cudaSetDevice(device));
+    FCK(cudaMalloc((void **)&mom, (size_t)nstreams * std::max(nblk, 1) * sizeof(uint4)));
+    FCK(cudaMalloc((void **)&vals, (size_t)nstreams * std::max(nblk, 1) * sizeof(uint2)));
+    FCK(cudaEventCreate(&e0));
+    FCK(cudaEventCreate(&e1));
+    FCK(cudaEventRecord(e0, 0));
+    launch_decimate(d_raw, n_iq, nstreams, stream_stride_bytes, mom, vals, dI, dQ, out_stride, max_out, 0);
+    FCK(cudaEventRecord(e1, 0));
+    FCK(cudaGetLastError());
+    FCK(cudaEventSynchronize(e1));
+    FCK(cudaEventElapsedTime(&g_fe_last_ms, e0, e1));
+    rc = std::min(nblk, max_out);
+done:
+    if (mom) cudaFree(mom);
+    if (vals) cudaFree(vals);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" int wspr_decimate_batch(const uint8_t *raw, int nstreams, size_t n_iq, float *I, float *Q, int max_out, int device) {
+    if (nstreams < 0 || !raw || !I || !Q || max_out < 0) return fe_fail(WSPR_ERR_ARG, "wspr_decimate_batch: bad arguments");
+    if (nstreams == 0 || max_out == 0) return 0;
+    int rc = WSPR_OK, nout = 0;
+    const size_t bytes = 2 * n_iq, stride = (bytes + 15) / 16 * 16 + 16;
+    // bound device memory: at most ~8 GiB of raw samples resident at a time
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstreams, ((size_t)8 << 30) / std::max<size_t>(stride, 1)));
+    uint8_t *d_raw = nullptr;
+    float *dI = nullptr, *dQ = nullptr;
+    if (device >= 0) FCK(cudaSetDevice(device));
+    FCK(cudaMalloc((void **)&d_raw, (size_t)chunk * stride));
+    FCK(cudaMalloc((void **)&dI, (size_t)chunk * max_out * sizeof(float)));
+    FCK(cudaMalloc((void **)&dQ, (size_t)chunk * max_out * sizeof(float)));
+    for (int s0 = 0; s0 < nstreams; s0 += chunk) {
+        const int n = std::min(chunk, nstreams - s0);
+        FCK(cudaMemset(d_raw, 0x80, (size_t)n * stride));
+        if (bytes) FCK(cudaMemcpy2D(d_raw, stride, raw + (size_t)s0 * bytes, bytes, bytes, n, cudaMemcpyHostToDevice));
+        nout = wspr_decimate_device(d_raw, n, n_iq, stride, dI, dQ, max_out, max_out, -1);
+        if (nout < 0) { rc = nout; goto done; }
+        FCK(cudaMemcpy(I + (size_t)s0 * max_out, dI, (size_t)n * max_out * sizeof(float), cudaMemcpyDeviceToHost));
+        FCK(cudaMemcpy(Q + (size_t)s0 * max_out, dQ, (size_t)n * max_out * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    rc = nout;
+done:
+    if (d_raw) cudaFree(d_raw);
+    if (dI) cudaFree(dI);
+    if (dQ) cudaFree(dQ);
+    return rc;
+}

@@ -13,7 +13,8 @@
 namespace wspr {
 
 static unsigned long long g_launches = 0;
-unsigned long long kernel_launch_count() { return g_launches; }
+extern unsigned long long g_frontend_launches;   // wspr_frontend.cu
+unsigned long long kernel_launch_count() { return g_launches + g_frontend_launches; }
 #define LAUNCHED() (++g_launches)
 
 // ---- constant tables ----------------------------------------------------------------------------------
@@ -22,7 +23,7 @@ __constant__ float c_lpf_w[NFILT];
 __constant__ float c_lpf_psum[NFILT];
 __constant__ float c_min_snr;
 __constant__ float c_floor_snr;
-__constant__ short c_mettab[512] = WSPR_METTAB_FLAT;
+__constant__ short c_mettab[2][256] = WSPR_METTAB_INIT;
 __device__ const double g_tw[256][2] = FFT512_TWIDDLE_INIT;
 
 void upload_tables(const HostTables &t) {
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(32) k_fano(Attempt *__restrict__ att, int natt
     unsigned metric, cycles, maxnp;
     unsigned char data[12];
     for (int k = 0; k < 12; k++) data[k] = 0;
-    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, c_mettab, delta, maxcycles);
+    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles);
     a.ok = (rc == 0);
     a.cycles = cycles;
     for (int k = 0; k < 12; k++) a.dec[k] = data[k];

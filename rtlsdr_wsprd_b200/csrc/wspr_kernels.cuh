@@ -143,7 +143,7 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
                          int lagmax, int lagstep, float drift, float4 *P, cudaStream_t st);
 
 // front end (rtlsdr_wsprd.c:126-244)
-void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint32_t *blocksums,
+void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, uint2 *vals,
                      float *I, float *Q, int out_stride, int max_out, cudaStream_t st);
 int decimate_outputs(size_t n_iq);
 
