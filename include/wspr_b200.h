@@ -120,7 +120,10 @@ int wspr_ctx_download(wspr_ctx *ctx, struct decoder_results *out, int *n_results
 /* device time of the last wspr_ctx_decode in ms (CUDA events on the context's stream) and kernels launched so far */
 float wspr_ctx_last_decode_ms(wspr_ctx *ctx);
 unsigned long long wspr_kernel_launches(void);
-/* kernel-level timing of the last decode: accumulated ms of the sync/demodulate correlation kernels */
+/* kernel-level timing of the last decode (enable with wspr_ctx_time_kernels(ctx, 1); adds a stream synchronisation per
+ * wave, so leave it off for throughput runs): accumulated ms of the mode-0 sync correlation kernel, its launch count
+ * and the (lag, symbol) cells it evaluated */
+int wspr_ctx_time_kernels(wspr_ctx *ctx, int on);
 float wspr_ctx_last_sync_ms(wspr_ctx *ctx);
 int wspr_ctx_last_sync_launches(wspr_ctx *ctx);
 double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
@@ -138,6 +141,9 @@ int wspr_decimate_batch(const uint8_t *raw, int nstreams, size_t n_iq, float *I,
 /* same with device-resident input/output (device pointers) */
 int wspr_decimate_device(const uint8_t *d_raw, int nstreams, size_t n_iq, size_t stream_stride_bytes, float *dI,
                          float *dQ, int out_stride, int max_out, int device);
+/* device time (ms, CUDA events) of the kernels of the last wspr_decimate_device call; text of the last front-end error */
+float wspr_decimate_last_ms(void);
+const char *wspr_frontend_last_error(void);
 
 #ifdef __cplusplus
 }

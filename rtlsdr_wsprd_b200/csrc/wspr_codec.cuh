@@ -247,6 +247,7 @@ WHD_NOINLINE int fano_decode(unsigned *metric_out, unsigned *cycles_out, unsigne
     short tm[FANO_MAXBITS][2];
     unsigned char sel[FANO_MAXBITS];
     const int last = (int)nbits - 1, tail = (int)nbits - 31;
+    for (unsigned n = 0; n <= nbits; n++) enc[n] = 0;   // nodes never reached read as zero in the output bytes
     for (unsigned n = 0; n < nbits; n++) {
         int a0 = mettab[symbols[2 * n]], a1 = mettab[256 + symbols[2 * n]];
         int b0 = mettab[symbols[2 * n + 1]], b1 = mettab[256 + symbols[2 * n + 1]];

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libwsprd_b200.so) against the oracle and the committed golden
+vectors.  Bar: every field of every spot identical (the contract in BASELINE.json demands callsign/locator/dBm and spot
+count bit-for-bit and soft symbols within 1e-5; the implementation is exact-order float, so these tests pin bit
+equality, tolerance 0), post-subtraction samples bit-identical, decimator outputs bit-identical."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+import rtlsdr_wsprd_b200 as w
+from rtlsdr_wsprd_b200 import corpus
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+FP = C.POINTER(C.c_float)
+UP = C.POINTER(C.c_ubyte)
+SOFT_SYMBOL_TOLERANCE = 0.0     # allowed |difference| of soft symbols (BASELINE allows 1e-5 * symfac)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(H.GOLDEN, "golden_decode.json")) as f:
+        return json.load(f)["cases"]
+
+
+def assert_matches_gold(case, r, io=None, qo=None):
+    g = case["spots"]
+    assert len(r) == len(g), (len(r), len(g), H.spot_lines(r), [y["line"] for y in g])
+    for x, y in zip(r, g):
+        assert (x["message"].decode(), x["call"].decode(), x["loc"].decode(), x["pwr"].decode()) == \
+            (y["message"], y["call"], y["loc"], y["pwr"])
+        assert w.spot_line(x) == y["line"]
+        assert float(x["freq"]).hex() == y["freq"] and float(x["snr"]).hex() == y["snr"]
+        assert float(x["dt"]).hex() == y["dt"] and float(x["sync"]).hex() == y["sync"]
+        assert float(x["drift"]) == y["drift"] and int(x["jitter"]) == y["jitter"] and int(x["cycles"]) == y["cycles"]
+    if io is not None:
+        assert sha(io) == case["i_sha"] and sha(qo) == case["q_sha"]
+
+
+def gpu_decode(I, Q, options=None, samples=True):
+    with w.BatchDecoder(len(I), I.shape[1]) as d:
+        d.upload(I, Q)
+        d.decode(options)
+        return d.download(samples=samples)
+
+
+def assert_batch_equals_oracle(I, Q, options=None):
+    spots, n, Io, Qo = gpu_decode(I, Q, options)
+    total = 0
+    for c in range(len(I)):
+        a, ia, qa = po.decode(po.oracle(), I[c], Q[c], options)
+        b = spots[c, : n[c]]
+        assert H.results_equal(a, b), (c, H.diff_results(a, b))
+        assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c]), c
+        total += len(a)
+    return total
+
+
+def test_loaded_library_is_the_in_tree_cuda_build():
+    assert os.path.samefile(w.library_path(), os.path.join(H.ROOT, "rtlsdr_wsprd_b200", "libwsprd_b200.so"))
+    before = w.kernel_launches()
+    gpu_decode(*H.make_corpus(2, 1)[:2])
+    assert w.kernel_launches() > before
+
+
+def test_reference_fixture_through_reference_abi(gold):
+    """config 1: signals/refSignalSnr0dB.iq through wspr_decode(); idat/qdat mutated like the reference does."""
+    i, q = w.read_iq_file(os.path.join(H.GOLDEN, "refSignalSnr0dB.iq"))
+    r = w.wspr_decode(i, q, 45000, w.default_options())
+    assert H.spot_lines(r) == [" -0.07   0.01 144.490550  0    K1JT   FN20 20"]   # documentation/bug-fix/REPORT.md:202
+    assert_matches_gold(gold["fixture"][0], r, i, q)
+
+
+@pytest.mark.parametrize("cfg", [2, 3])
+def test_golden_corpus(gold, cfg):
+    cases = gold["config%d" % cfg]
+    I, Q, _ = H.make_corpus(cfg, len(cases))
+    spots, n, Io, Qo = gpu_decode(I, Q)
+    for c, case in enumerate(cases):
+        assert_matches_gold(case, spots[c, : n[c]], Io[c], Qo[c])
+
+
+@pytest.mark.parametrize("name,opt", [("quick", dict(quickmode=1)), ("single", dict(npasses=1, subtraction=0))])
+def test_golden_option_variants(gold, name, opt):
+    I, Q, _ = H.make_corpus(3, 4)
+    spots, n, Io, Qo = gpu_decode(I, Q, w.default_options(**opt))
+    for c in range(4):
+        assert_matches_gold(gold["config3_" + name][c], spots[c, : n[c]], Io[c], Qo[c])
+
+
+def test_config2_against_oracle():
+    I, Q, _ = H.make_corpus(2, 48, start=500)
+    assert assert_batch_equals_oracle(I, Q) >= 40
+
+
+def test_config3_against_oracle():
+    I, Q, _ = H.make_corpus(3, 16, start=500)
+    assert assert_batch_equals_oracle(I, Q) >= 140
+
+
+def test_weak_signals_exercise_jitter_search_and_fano_timeouts():
+    """SNR -31..-25 dB: most candidates fail at jitter 0, go through the 42 further attempts and many Fano timeouts."""
+    n = 4
+    I = np.zeros((n, corpus.NSAMP), np.float32)
+    Q = np.zeros_like(I)
+    for c in range(n):
+        plan = corpus.ten_signal_plan(900 + c, snrs=np.arange(-31.0, -24.0, 1.0))
+        I[c], Q[c] = corpus.make_capture(7, 900 + c, plan, H.channel_symbols)
+    spots, n_res, Io, Qo = gpu_decode(I, Q)
+    jit = 0
+    for c in range(n):
+        a, ia, qa = po.decode(po.oracle(), I[c], Q[c])
+        assert H.results_equal(a, spots[c, : n_res[c]]), (c, H.diff_results(a, spots[c, : n_res[c]]))
+        assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c])
+        jit += int(np.count_nonzero(a["jitter"]))
+    assert jit > 0, "corpus did not exercise the jitter path"
+
+
+def test_drifting_and_edge_timed_signals():
+    I = np.zeros((6, corpus.NSAMP), np.float32)
+    Q = np.zeros_like(I)
+    plans = [[dict(message="K1JT FN20 20", f0=30.0, dt0=0.3, snr=-15.0, drift=-3.0)],
+             [dict(message="W1AW FN31 37", f0=-72.5, dt0=-0.9, snr=-18.0, drift=2.0)],
+             [dict(message="G4JNT IO90 10", f0=108.0, dt0=1.4, snr=-12.0)],              # band edge + late start
+             [dict(message="PJ4/K1ABC 37", f0=10.0, dt0=0.0, snr=-14.0),                 # type 2, then type 3 that
+              dict(message="<PJ4/K1ABC> FK52UD 37", f0=55.0, dt0=0.1, snr=-19.0)],       # needs the hash of the first
+             [dict(message="K9AN EN50 33", f0=0.0, dt0=0.0, snr=-5.0), dict(message="K9AN EN50 33", f0=1.5, dt0=0.0, snr=-8.0)],
+             []]                                                                           # noise only
+    for c, plan in enumerate(plans):
+        I[c], Q[c] = corpus.make_capture(8, c, plan, H.channel_symbols)
+    assert assert_batch_equals_oracle(I, Q) >= 5
+
+
+def test_degenerate_inputs():
+    z = np.zeros((3, corpus.NSAMP), np.float32)
+    I, Q = z.copy(), z.copy()
+    I[1], Q[1] = 0.25, -0.25                                      # DC
+    t = np.arange(corpus.NSAMP)
+    I[2] = (0.5 * np.cos(2 * np.pi * 20.0 * t / 375.0)).astype(np.float32)   # noise-free carrier
+    Q[2] = (0.5 * np.sin(2 * np.pi * 20.0 * t / 375.0)).astype(np.float32)
+    assert_batch_equals_oracle(I[1:], Q[1:])
+    spots, n, Io, Qo = gpu_decode(I[:1], Q[:1])                  # all-zero capture: 0/0 everywhere, no spots
+    a, _, _ = po.decode(po.oracle(), I[0], Q[0])
+    assert n[0] == len(a) == 0
+    with w.BatchDecoder(4) as d:                                  # empty batch
+        d.upload(np.zeros((0, corpus.NSAMP), np.float32), np.zeros((0, corpus.NSAMP), np.float32))
+        d.decode()
+        spots, n = d.download()
+        assert spots.shape[0] == 0 and n.shape[0] == 0
+
+
+def test_short_capture_length():
+    I, Q, _ = H.make_corpus(2, 3, start=40)
+    I, Q = np.ascontiguousarray(I[:, :43000]), np.ascontiguousarray(Q[:, :43000])
+    assert_batch_equals_oracle(I, Q)
+
+
+def test_results_independent_of_batch_composition():
+    """1024-capture batch = 32 distinct captures, each 32 times in shuffled order: every replica decodes identically
+    (and equal to the oracle on the distinct captures) -- batch-scale indexing at BASELINE config-2 size."""
+    I0, Q0, _ = H.make_corpus(3, 8, start=300)
+    I1, Q1, _ = H.make_corpus(2, 24, start=300)
+    I0, Q0 = np.concatenate([I0, I1]), np.concatenate([Q0, Q1])
+    order = np.random.default_rng(0).permutation(np.repeat(np.arange(32), 32))
+    spots, n, Io, Qo = gpu_decode(I0[order], Q0[order])
+    ref = {}
+    for k in range(32):
+        a, ia, qa = po.decode(po.oracle(), I0[k], Q0[k])
+        ref[k] = (a, sha(ia), sha(qa))
+    for pos, k in enumerate(order):
+        a, si, sq = ref[int(k)]
+        assert H.results_equal(a, spots[pos, : n[pos]]), (pos, k)
+        assert sha(Io[pos]) == si and sha(Qo[pos]) == sq
+
+
+def test_one_shot_batch_entry_and_normalise():
+    I, Q, _ = H.make_corpus(2, 5, start=60)
+    res = w.decode_batch(I, Q)
+    for c in range(5):
+        a, _, _ = po.decode(po.oracle(), I[c], Q[c])
+        assert H.results_equal(a, res[c])
+    # hand-off normalisation (rtlsdr_wsprd.c:291-305) on the device == oracle_normalise
+    raw_i, raw_q = (I * 3.7).astype(np.float32), (Q * 3.7).astype(np.float32)
+    with w.BatchDecoder(5) as d:
+        d.upload(raw_i, raw_q)
+        d.normalise()
+        d.decode(w.default_options(npasses=1, subtraction=0))
+        _, _, In, Qn = d.download(samples=True)
+    orc = po.oracle()
+    for c in range(5):
+        a, b = raw_i[c].copy(), raw_q[c].copy()
+        orc.oracle_normalise(a.ctypes.data_as(FP), b.ctypes.data_as(FP), a.shape[0])
+        assert np.array_equal(a, In[c]) and np.array_equal(b, Qn[c])
+
+
+def test_stage_spectrogram_and_candidates_bit_exact():
+    orc = po.oracle()
+    orc.oracle_spectrogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    orc.oracle_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    orc.oracle_candidates.restype = C.c_int
+    I, Q, _ = H.make_corpus(3, 6, start=700)
+    with w.BatchDecoder(6) as d:
+        d.upload(I, Q)
+        ps = d.spectrogram()
+        for maxdrift in (4, 0):
+            cands, npk, sm = d.candidates(maxdrift, want_smspec=True)
+            for c in range(6):
+                pso = np.zeros((512, ps.shape[2]), np.float32)
+                orc.oracle_spectrogram(I[c].ctypes.data, Q[c].ctypes.data, I.shape[1], pso.ctypes.data)
+                assert np.array_equal(ps[c], pso)
+                co, smo = np.zeros(200, w.CAND_DTYPE), np.zeros(411, np.float32)
+                nk = orc.oracle_candidates(pso.ctypes.data, ps.shape[2], maxdrift, co.ctypes.data, smo.ctypes.data)
+                assert nk == npk[c] and cands[c, :nk].tobytes() == co[:nk].tobytes()
+                assert np.array_equal(sm[c], smo)
+
+
+def test_sync_and_demodulate_abi_against_reference_golden():
+    """soft symbols: tolerance SOFT_SYMBOL_TOLERANCE (= 0, BASELINE allows 1e-5); sync/freq/shift identical."""
+    st = np.load(os.path.join(H.GOLDEN, "golden_stages.npz"))
+    lib = w.library()
+    I, Q, _ = H.make_corpus(3, 1)
+    i0, q0 = I[0].copy(), Q[0].copy()
+    for k in range(3):
+        for dft in (0, 1):
+            f1, sh, drift = st["sync_%d_%d_in" % (k, dft)]
+            freq, shift, dr, sync = C.c_float(f1), C.c_int(int(sh)), C.c_float(drift), C.c_float(0)
+            sym = (C.c_ubyte * 162)()
+            a = (i0.ctypes.data_as(FP), q0.ctypes.data_as(FP), 45000, sym, C.byref(freq))
+            lib.sync_and_demodulate(*a, 0, 0, 0.0, C.byref(shift), shift.value - 128, shift.value + 128, 8, C.byref(dr), 50, C.byref(sync), 0)
+            assert np.array_equal(np.array([freq.value, shift.value, sync.value]), st["sync_%d_%d_m0" % (k, dft)])
+            lib.sync_and_demodulate(*a, -2, 2, 0.1, C.byref(shift), shift.value, shift.value, 1, C.byref(dr), 50, C.byref(sync), 1)
+            assert np.array_equal(np.array([freq.value, shift.value, sync.value]), st["sync_%d_%d_m1" % (k, dft)])
+            lib.sync_and_demodulate(*a, 0, 0, 0.0, C.byref(shift), shift.value, shift.value, 1, C.byref(dr), 50, C.byref(sync), 2)
+            assert sync.value == st["sync_%d_%d_m2" % (k, dft)][0]
+            got = np.frombuffer(bytes(sym), np.uint8).astype(np.float64)
+            assert np.max(np.abs(got - st["sync_%d_%d_sym" % (k, dft)])) <= SOFT_SYMBOL_TOLERANCE
+
+
+def test_subtract_signal2_abi_against_reference_golden():
+    st = np.load(os.path.join(H.GOLDEN, "golden_stages.npz"))
+    lib = w.library()
+    I, Q, _ = H.make_corpus(3, 1)
+    chan = st["sub_chan"]
+    for dft in (0, -1):
+        f1, sh, drift = st["sub_%d_in" % dft]
+        ia, qa = I[0].copy(), Q[0].copy()
+        lib.subtract_signal2(ia.ctypes.data_as(FP), qa.ctypes.data_as(FP), 45000, C.c_float(f1), int(sh), C.c_float(drift),
+                             chan.ctypes.data_as(UP))
+        assert np.array_equal(ia, st["sub_%d_i" % dft]) and np.array_equal(qa, st["sub_%d_q" % dft])
+
+
+# ---- front end ----------------------------------------------------------------------------------------------------
+def oracle_decimate(raw, n_iq, max_out):
+    orc = po.oracle()
+    orc.oracle_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    io, qo = np.zeros(max_out, np.float32), np.zeros(max_out, np.float32)
+    n = orc.oracle_decimate(raw.ctypes.data, n_iq, io.ctypes.data, qo.ctypes.data, max_out)
+    return io, qo, n
+
+
+def test_frontend_against_reference_golden():
+    from test_oracle_vs_ref import frontend_golden_streams
+    raw, n_iq, fe = frontend_golden_streams()
+    Ig, Qg, n = w.decimate_batch(raw, max_out=128)
+    assert n == 70
+    for s in range(3):
+        assert np.array_equal(Ig[s, :n], fe["i%d" % s]) and np.array_equal(Qg[s, :n], fe["q%d" % s])
+        assert not Ig[s, n:].any() and not Qg[s, n:].any()
+
+
+@pytest.mark.parametrize("n_iq", [0, 5, 6400, 6401, 6402, 6401 * 37 + 6400, 6401 * 300 + 8])
+def test_frontend_ragged_lengths_against_oracle(n_iq):
+    rng = np.random.default_rng(n_iq)
+    raw = rng.integers(0, 256, size=(4, 2 * n_iq), dtype=np.uint8)
+    if n_iq:
+        raw[0, :] = 0          # rail: int8 negation wrap on every negated sample
+        raw[1, :] = 255
+    Ig, Qg, n = w.decimate_batch(raw, n_iq=n_iq, max_out=320)
+    assert n == min(n_iq // 6401, 320)
+    for s in range(4):
+        io, qo, no = oracle_decimate(raw[s], n_iq, 320)
+        assert no == n and np.array_equal(io, Ig[s]) and np.array_equal(qo, Qg[s])
+
+
+def test_frontend_full_length_stream_then_decode():
+    """BASELINE config 4 at full size: one 120 s stream (288 000 000 IQ pairs, 576 MB) -> 44 992 samples, bit-identical
+    to the oracle; then hand-off normalisation + decode finds the embedded signal."""
+    n_iq = 288_000_000
+    sym = H.channel_symbols("K1JT FN20 20")
+    raw = corpus.make_raw_stream(4, 0, n_iq, f0=37.0, snr=-8.0, symbols=sym)
+    Ig, Qg, n = w.decimate_batch(raw[None, :], max_out=corpus.NSAMP)
+    assert n == 44992
+    io, qo, no = oracle_decimate(raw, n_iq, corpus.NSAMP)
+    assert no == n and np.array_equal(io, Ig[0]) and np.array_equal(qo, Qg[0])
+    with w.BatchDecoder(1) as d:
+        d.upload(Ig, Qg)
+        d.normalise()
+        d.decode()
+        spots, nres = d.download()
+    a, b = io.copy(), qo.copy()
+    po.oracle().oracle_normalise(a.ctypes.data_as(FP), b.ctypes.data_as(FP), a.shape[0])
+    r, _, _ = po.decode(po.oracle(), a, b)
+    assert H.results_equal(r, spots[0, : nres[0]])
+    assert nres[0] >= 1 and spots[0, 0]["message"] == b"K1JT FN20 20"

@@ -1,0 +1,185 @@
+"""Pins the oracle (oracle/wspr_oracle.c, our CPU restatement) against the reference: its golden spot lines, its own
+unit tests, the committed golden vectors generated from the compiled reference (tools/make_golden.py) and -- where
+/root/reference or a prebuilt oracle/_ref is available -- the compiled reference itself on seeded captures."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+import helpers as H
+
+FP = C.POINTER(C.c_float)
+UP = C.POINTER(C.c_ubyte)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(H.GOLDEN, "golden_decode.json")) as f:
+        return json.load(f)["cases"]
+
+
+def check_against_gold(case, r, io, qo):
+    g = case["spots"]
+    assert len(r) == len(g)
+    for x, y in zip(r, g):
+        assert x["message"].decode() == y["message"] and x["call"].decode() == y["call"]
+        assert x["loc"].decode() == y["loc"] and x["pwr"].decode() == y["pwr"]
+        assert float(x["freq"]).hex() == y["freq"] and float(x["snr"]).hex() == y["snr"]
+        assert float(x["dt"]).hex() == y["dt"] and float(x["sync"]).hex() == y["sync"]
+        assert float(x["drift"]) == y["drift"] and int(x["jitter"]) == y["jitter"] and int(x["cycles"]) == y["cycles"]
+        assert po.spot_line(x) == y["line"]
+    assert sha(io) == case["i_sha"] and sha(qo) == case["q_sha"]
+
+
+def test_golden_fixture_line_oracle(gold):
+    # documentation/bug-fix/REPORT.md:202 -- the reference's documented output for its own fixture
+    i, q = po.read_iq_file(os.path.join(H.GOLDEN, "refSignalSnr0dB.iq"))
+    r, io, qo = po.decode(po.oracle(), i, q)
+    assert H.spot_lines(r) == [" -0.07   0.01 144.490550  0    K1JT   FN20 20"]
+    check_against_gold(gold["fixture"][0], r, io, qo)
+
+
+@pytest.mark.parametrize("cfg,count", [(2, 16), (3, 8)])
+def test_oracle_reproduces_reference_golden(gold, cfg, count):
+    I, Q, _ = H.make_corpus(cfg, count)
+    for c in range(count):
+        case = gold["config%d" % cfg][c]
+        assert sha(I[c]) == case["in_sha"], "corpus generator drifted from the committed golden inputs"
+        r, io, qo = po.decode(po.oracle(), I[c], Q[c])
+        check_against_gold(case, r, io, qo)
+
+
+@pytest.mark.parametrize("name,opt", [("quick", dict(quickmode=1)), ("single", dict(npasses=1, subtraction=0))])
+def test_oracle_options_variants(gold, name, opt):
+    I, Q, _ = H.make_corpus(3, 2)
+    for c in range(2):
+        r, io, qo = po.decode(po.oracle(), I[c], Q[c], po.default_options(**opt))
+        check_against_gold(gold["config3_" + name][c], r, io, qo)
+
+
+def test_oracle_stage_golden():
+    """sync_and_demodulate (three modes, with and without drift) and subtract_signal2 vs compiled-reference outputs."""
+    st = np.load(os.path.join(H.GOLDEN, "golden_stages.npz"))
+    orc = po.oracle()
+    orc.sync_and_demodulate.restype = None
+    orc.sync_and_demodulate.argtypes = [FP, FP, C.c_long, UP, FP, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.c_int,
+                                        C.c_int, C.c_int, FP, C.c_int, FP, C.c_int]
+    orc.subtract_signal2.restype = None
+    orc.subtract_signal2.argtypes = [FP, FP, C.c_long, C.c_float, C.c_int, C.c_float, UP]
+    I, Q, _ = H.make_corpus(3, 1)
+    i0, q0 = I[0].copy(), Q[0].copy()
+    for k in range(3):
+        for d in (0, 1):
+            f1, sh, drift = st["sync_%d_%d_in" % (k, d)]
+            freq, shift, dr, sync = C.c_float(f1), C.c_int(int(sh)), C.c_float(drift), C.c_float(0)
+            sym = (C.c_ubyte * 162)()
+            a = (i0.ctypes.data_as(FP), q0.ctypes.data_as(FP), 45000, sym, C.byref(freq))
+            orc.sync_and_demodulate(*a, 0, 0, 0.0, C.byref(shift), shift.value - 128, shift.value + 128, 8, C.byref(dr), 50, C.byref(sync), 0)
+            assert np.array_equal(np.array([freq.value, shift.value, sync.value]), st["sync_%d_%d_m0" % (k, d)])
+            orc.sync_and_demodulate(*a, -2, 2, 0.1, C.byref(shift), shift.value, shift.value, 1, C.byref(dr), 50, C.byref(sync), 1)
+            assert np.array_equal(np.array([freq.value, shift.value, sync.value]), st["sync_%d_%d_m1" % (k, d)])
+            orc.sync_and_demodulate(*a, 0, 0, 0.0, C.byref(shift), shift.value, shift.value, 1, C.byref(dr), 50, C.byref(sync), 2)
+            assert sync.value == st["sync_%d_%d_m2" % (k, d)][0]
+            assert np.array_equal(np.frombuffer(bytes(sym), np.uint8), st["sync_%d_%d_sym" % (k, d)])
+    chan = st["sub_chan"]
+    for d in (0, -1):
+        f1, sh, drift = st["sub_%d_in" % d]
+        ia, qa = i0.copy(), q0.copy()
+        orc.subtract_signal2(ia.ctypes.data_as(FP), qa.ctypes.data_as(FP), 45000, C.c_float(f1), int(sh), C.c_float(drift),
+                             chan.ctypes.data_as(UP))
+        assert np.array_equal(ia, st["sub_%d_i" % d]) and np.array_equal(qa, st["sub_%d_q" % d])
+
+
+def frontend_golden_streams():
+    fe = np.load(os.path.join(H.GOLDEN, "golden_frontend.npz"))
+    seed, n_iq = [int(v) for v in fe["seed"]]
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, size=(3, 2 * n_iq), dtype=np.uint8)
+    raw[1, : 2 * 6401 * 8] = 0
+    raw[2, ::5] = 0
+    raw[2, 1::3] = 255
+    return raw, n_iq, fe
+
+
+def test_oracle_frontend_golden():
+    raw, n_iq, fe = frontend_golden_streams()
+    orc = po.oracle()
+    orc.oracle_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    for s in range(3):
+        io, qo = np.zeros(128, np.float32), np.zeros(128, np.float32)
+        n = orc.oracle_decimate(raw[s].ctypes.data, n_iq, io.ctypes.data, qo.ctypes.data, 128)
+        assert n == len(fe["i%d" % s]) == n_iq // 6401
+        assert np.array_equal(io[:n], fe["i%d" % s]) and np.array_equal(qo[:n], fe["q%d" % s])
+
+
+def test_fano_and_unpack_known_answers_oracle():
+    """tests/test_wsprd.c:168-220 (encode -> 0/255 soft symbols -> fano) and :345-384 (unpk_ -> K1JT FN20 20)."""
+    orc = po.oracle()
+    sym = H.channel_symbols("K1JT FN20 20", orc)
+    soft = np.where(sym >> 1, 255, 0).astype(np.uint8)
+    orc.deinterleave(soft.ctypes.data_as(UP))
+    mettab = ((C.c_int * 256) * 2)()
+    orc.oracle_mettab(mettab)
+    metric, cycles, maxnp = C.c_uint(), C.c_uint(), C.c_uint()
+    data = (C.c_ubyte * 12)()
+    rc = orc.fano(C.byref(metric), C.byref(cycles), C.byref(maxnp), data, soft.ctypes.data_as(UP), 81, mettab, 60, 10000)
+    assert rc == 0 and cycles.value == 82
+    msg = (C.c_byte * 12)(*[(b - 256 if b > 127 else b) for b in bytes(data)])
+    ht, lt = C.create_string_buffer(32768 * 13), C.create_string_buffer(32768 * 5)
+    clp, call, loc, pwr, cs = (C.create_string_buffer(n) for n in (23, 13, 7, 3, 13))
+    assert orc.unpk_(msg, ht, lt, clp, call, loc, pwr, cs) == 0
+    assert (clp.value, call.value, loc.value, pwr.value) == (b"K1JT FN20 20", b"K1JT", b"FN20", b"20")
+
+
+# ---- against the compiled reference itself (this container; prebuilt oracle/_ref elsewhere) ----------------------
+needs_ref = pytest.mark.skipif(not po.ref_available(), reason="no /root/reference and no prebuilt oracle/_ref")
+
+
+@needs_ref
+def test_reference_unit_tests_pass():
+    exe = os.path.join(po.HERE, "_ref", "test_wsprd_ref")
+    po.ref()
+    if not os.path.exists(exe):
+        pytest.skip("reference test binary not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout[-2000:]
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg,start,count", [(2, 100, 6), (3, 100, 4)])
+def test_oracle_equals_compiled_reference(cfg, start, count):
+    ref = po.ref()
+    I, Q, _ = H.make_corpus(cfg, count, start=start)
+    for c in range(count):
+        a, ia, qa = po.decode(ref, I[c], Q[c])
+        b, ib, qb = po.decode(po.oracle(), I[c], Q[c])
+        assert H.results_equal(a, b), H.diff_results(a, b)
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb)
+
+
+@needs_ref
+def test_oracle_frontend_equals_reference_callback():
+    if not os.path.exists(os.path.join(po.HERE, "_ref", "libfrontend_ref.so")):
+        pytest.skip("reference front end not built")
+    rng = np.random.default_rng(11)
+    n_iq = 6401 * 40 + 3000
+    raw = rng.integers(0, 256, size=2 * n_iq, dtype=np.uint8)
+    raw[5000:9000] = 0
+    f = po.RefFrontend()
+    f.push(raw)
+    ir, qr = f.read()
+    orc = po.oracle()
+    orc.oracle_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    io, qo = np.zeros(64, np.float32), np.zeros(64, np.float32)
+    n = orc.oracle_decimate(raw.ctypes.data, n_iq, io.ctypes.data, qo.ctypes.data, 64)
+    assert n == len(ir) == 40
+    assert np.array_equal(io[:n], ir) and np.array_equal(qo[:n], qr)
