@@ -119,6 +119,8 @@ int wspr_ctx_decode(wspr_ctx *ctx, struct decoder_options options);
 int wspr_ctx_download(wspr_ctx *ctx, struct decoder_results *out, int *n_results, float *I_out, float *Q_out);
 /* device time of the last wspr_ctx_decode in ms (CUDA events on the context's stream) and kernels launched so far */
 float wspr_ctx_last_decode_ms(wspr_ctx *ctx);
+/* the cudaStream_t all of the context's copies and kernels are issued on (for callers that record their own events) */
+void *wspr_ctx_stream(wspr_ctx *ctx);
 unsigned long long wspr_kernel_launches(void);
 /* kernel-level timing of the last decode (enable with wspr_ctx_time_kernels(ctx, 1); adds a stream synchronisation per
  * wave, so leave it off for throughput runs): accumulated ms of the mode-0 sync correlation kernel, its launch count

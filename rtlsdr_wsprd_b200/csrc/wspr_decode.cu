@@ -342,6 +342,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
 }
 
 extern "C" float wspr_ctx_last_decode_ms(wspr_ctx *c) { return c ? c->last_ms : 0.0f; }
+extern "C" void *wspr_ctx_stream(wspr_ctx *c) { return c ? (void *)c->st : nullptr; }
 extern "C" float wspr_ctx_last_sync_ms(wspr_ctx *c) { return c ? c->sync_ms : 0.0f; }
 extern "C" int wspr_ctx_last_sync_launches(wspr_ctx *c) { return c ? c->sync_launches : 0; }
 extern "C" double wspr_ctx_last_sync_cells(wspr_ctx *c) { return c ? c->sync_cells : 0.0; }

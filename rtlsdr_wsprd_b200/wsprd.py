@@ -101,6 +101,8 @@ def library():
     lib.wspr_ctx_last_decode_ms.restype = C.c_float
     lib.wspr_ctx_last_decode_ms.argtypes = [vp]
     lib.wspr_ctx_time_kernels.argtypes = [vp, C.c_int]
+    lib.wspr_ctx_stream.restype = vp
+    lib.wspr_ctx_stream.argtypes = [vp]
     lib.wspr_ctx_last_sync_ms.restype = C.c_float
     lib.wspr_ctx_last_sync_ms.argtypes = [vp]
     lib.wspr_ctx_last_sync_launches.argtypes = [vp]
@@ -244,6 +246,10 @@ class BatchDecoder:
         _check(self.lib.wspr_ctx_candidates(self.ctx, int(maxdrift), cands.ctypes.data, npk.ctypes.data,
                                             sm.ctypes.data if want_smspec else None), "wspr_ctx_candidates")
         return (cands, npk, sm) if want_smspec else (cands, npk)
+
+    def stream(self):
+        """cudaStream_t (as int) the context issues its work on, e.g. for torch.cuda.ExternalStream."""
+        return int(self.lib.wspr_ctx_stream(self.ctx) or 0)
 
     def time_kernels(self, on=True):
         self.lib.wspr_ctx_time_kernels(self.ctx, int(bool(on)))
