@@ -119,6 +119,9 @@ int wspr_ctx_decode(wspr_ctx *ctx, struct decoder_options options);
 int wspr_ctx_download(wspr_ctx *ctx, struct decoder_results *out, int *n_results, float *I_out, float *Q_out);
 /* device time of the last wspr_ctx_decode in ms (CUDA events on the context's stream) and kernels launched so far */
 float wspr_ctx_last_decode_ms(wspr_ctx *ctx);
+/* scheduling statistics of the last decode: rounds driven, candidates finished on side streams */
+int wspr_ctx_last_rounds(wspr_ctx *ctx);
+int wspr_ctx_last_deferred(wspr_ctx *ctx);
 /* the cudaStream_t all of the context's copies and kernels are issued on (for callers that record their own events) */
 void *wspr_ctx_stream(wspr_ctx *ctx);
 unsigned long long wspr_kernel_launches(void);

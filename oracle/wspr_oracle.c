@@ -119,6 +119,9 @@ int encode(unsigned char *symbols, unsigned char *data, unsigned int nbytes) {
 /* fano.c:87-238.  Node arrays instead of a struct list; same moves, same cycle accounting:
  * returns 0 on success, -1 when the loop counter reached maxcycles*nbits (note: also when the
  * final forward move happened exactly on the last allowed cycle, fano.c:234). */
+/* instrumentation for scheduling studies (tools/oracle_stats.py); not part of any result */
+long oracle_stat[16];
+
 int fano(unsigned int *metric, unsigned int *cycles, unsigned int *maxnp, unsigned char *data,
          unsigned char *symbols, unsigned int nbits, int mettab[2][256], int delta, unsigned int maxcycles) {
     enum { MAXN = 256 };
@@ -834,6 +837,7 @@ int wspr_decode(float *idat, float *qdat, int samples, struct decoder_options op
         int npk = oracle_candidates(ps, blocks, maxdrift, cands, NULL);
 
         for (int j = 0; j < npk; j++) {                            /* wsprd.c:697-823 */
+            oracle_stat[0 + (ipass > 0)]++;                        /* candidates examined, per pass */
             memset(callsign, 0, 13);
             memset(call_loc_pow, 0, 23);
             memset(call, 0, 13);
@@ -852,6 +856,7 @@ int wspr_decode(float *idat, float *qdat, int samples, struct decoder_options op
             cands[j].drift = drift;
             cands[j].sync = sync;
             int worth = sync > minsync1;
+            oracle_stat[2 + (ipass > 0)] += worth;                 /* passed the minsync1 gate */
             int idt = 0, ii = 0, not_decoded = 1;
             while (worth && not_decoded && idt <= (128 / iifac)) {
                 ii = (idt + 1) / 2;
@@ -869,10 +874,19 @@ int wspr_decode(float *idat, float *qdat, int samples, struct decoder_options op
                 if (sync > minsync2 && rms > minrms) {
                     deinterleave(symbols);
                     not_decoded = fano(&metric, &cycles, &maxnp, decdata, symbols, OR_NBITS, mettab, delta, maxcycles);
+                    oracle_stat[4]++;                              /* Fano calls */
+                    oracle_stat[5] += not_decoded != 0;            /* ... that timed out */
+                    if (!not_decoded) {
+                        oracle_stat[6 + (idt > 0)]++;              /* decoded at jitter 0 / at a later jitter */
+                        if (cycles > 4096) oracle_stat[8]++;       /* successes needing more than 4096 / 32768 cycles */
+                        if (cycles > 32768) oracle_stat[9]++;
+                        if (idt > 0) oracle_stat[12] += idt;       /* sum of winning idt */
+                    }
                 }
                 idt++;
                 if (options.quickmode) break;
             }
+            if (worth && not_decoded) oracle_stat[10 + (ipass > 0)]++;   /* worth a try, never decoded (per pass) */
             if (!(worth && !not_decoded)) continue;
 
             for (int i = 0; i < 11; i++) message[i] = (signed char)(decdata[i] > 127 ? decdata[i] - 256 : decdata[i]);

@@ -235,11 +235,19 @@ WHD void interleave162(unsigned char *sym) {
 // Returns 0 on success, -1 on timeout (cycle counter reached maxcycles*nbits).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int FANO_MAXBITS = 128;
+constexpr int FANO_STOPPED = 2;      // return value: the run was cut short (budget reached or poll() asked to stop)
 
-template <typename MetT>
+// poll hook: called every 1024 cycles; returning true abandons the run (result FANO_STOPPED)
+struct FanoNoPoll {
+    WHD bool operator()(unsigned) const { return false; }
+};
+
+// stop_after: 0 = run to the reference's limit (maxcycles*nbits); otherwise give up with FANO_STOPPED once that many
+// cycles have been spent without finishing (a later full run from scratch reproduces the identical result).
+template <typename MetT, typename Poll = FanoNoPoll>
 WHD_NOINLINE int fano_decode(unsigned *metric_out, unsigned *cycles_out, unsigned *maxnp_out, unsigned char *data,
                              const unsigned char *symbols, unsigned nbits, const MetT *mettab /*[2][256]*/, int delta,
-                             unsigned maxcycles) {
+                             unsigned maxcycles, unsigned stop_after = 0, Poll poll = Poll()) {
     if (nbits > (unsigned)FANO_MAXBITS - 1 || nbits < 32) return -1;
     uint32_t enc[FANO_MAXBITS];
     int gam[FANO_MAXBITS];
@@ -267,8 +275,14 @@ WHD_NOINLINE int fano_decode(unsigned *metric_out, unsigned *cycles_out, unsigne
     sel[0] = 0;
     gam[0] = 0;
     const unsigned limit = maxcycles * nbits;
+    const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0;
     unsigned it;
+    bool stopped = false;
     for (it = 1; it <= limit; it++) {
+        if ((it & 1023u) == 0 && ((stop != 0 && it >= stop) || poll(it))) {
+            stopped = true;
+            break;
+        }
         if (pos > maxnp) maxnp = pos;
         int ng = gam[pos] + tm[pos][sel[pos]];
         if (ng >= thr) {
@@ -314,6 +328,7 @@ WHD_NOINLINE int fano_decode(unsigned *metric_out, unsigned *cycles_out, unsigne
     for (unsigned b = 0; b < (nbits >> 3); b++) data[b] = (unsigned char)enc[7 + 8 * b];
     *cycles_out = it + 1;
     *maxnp_out = (unsigned)maxnp;
+    if (stopped) return FANO_STOPPED;
     return (it >= limit) ? -1 : 0;
 }
 

@@ -3,9 +3,11 @@
 //
 // Scheduling: the reference walks the candidates of one capture serially because, in pass 0, every successful
 // decode is subtracted from the samples before the next candidate is examined (wsprd.c:781-789).  Captures are
-// independent, so the batch is processed in *waves*: wave r handles candidate rank r of every capture at once
-// (sync search -> soft symbols -> Fano -> unpack/resolve -> subtraction).  Where no subtraction can happen (pass
-// >= 1, or subtraction disabled) all ranks go into one wave and only the in-order resolve step stays sequential.
+// independent, so every capture runs its own state machine (wspr_kernels.cuh, enum Phase) and the host drives
+// *rounds*: each round advances every ready capture by one candidate (sync search -> soft symbols -> budgeted Fano
+// -> unpack/resolve -> subtraction) and runs the pass set-up (spectrogram, candidate search, coarse sync) for the
+// captures that enter a new pass.  The rare candidates that need a long Fano run or the 42-attempt jitter search
+// are finished on side streams while the rounds go on, so a straggler delays only its own capture.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -61,30 +63,45 @@ static void host_tables(HostTables &t) {
     t.floor_snr = 0.1 * t.min_snr;                                                // wsprd.c:595
 }
 
+constexpr int NSIDE = 12;          // side-stream slots for deferred candidates
+
+struct SideSlot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    int cap = 0;                   // scratch capacity in candidates
+    int *list = nullptr;           // [maxcap] deferred capture indices of one round
+    int *count = nullptr;          // device counter of the list
+    float4 *P2 = nullptr;          // [cap][42][162] tone powers of the jitter attempts
+    Attempt *att1 = nullptr;       // [cap][42]
+    int *jbest = nullptr;          // [cap] lowest successful jitter attempt so far
+};
+
 struct wspr_ctx {
     int device = 0, maxcap = 0, np = 0, stride = 0, blocks = 0;
     int ncap = 0;
-    int jobcap = 0, failcap = 0;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float *I = nullptr, *Q = nullptr, *psT = nullptr, *smspec = nullptr;
     Cand *cands = nullptr;
     CapState *caps = nullptr;
     Spot *spots = nullptr;
     int *nres = nullptr;
-    Job *jobs = nullptr;
-    int *jobmap = nullptr, *faillist = nullptr, *sublist = nullptr;
-    float4 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;
-    Attempt *att0 = nullptr, *att1 = nullptr;
+    Job *jobs = nullptr;           // [maxcap] the candidate each capture is working on
+    Attempt *att0 = nullptr;       // [maxcap] its jitter-0 attempt
+    int *ident = nullptr, *setup_list = nullptr, *job_list = nullptr, *res_list = nullptr, *sub_list = nullptr;
+    float4 *P0 = nullptr, *P1 = nullptr;
     float *phi0 = nullptr;
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
     Counters *h_cnt = nullptr;     // pinned host mirror
-    int *h_npk = nullptr;          // pinned host copy of per-capture candidate counts
+    SideSlot side[NSIDE];
     float last_ms = 0.0f, sync_ms = 0.0f;
-    int sync_launches = 0;
+    int sync_launches = 0, rounds = 0, deferred = 0;
     double sync_cells = 0.0;
     bool time_kernels = false;
+    std::vector<cudaEvent_t> kev;  // event pairs around the mode-0 sync kernel, one pair per round
+    std::vector<int> kev_jobs;
 };
 
 template <class T>
@@ -93,16 +110,22 @@ static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * s
 extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->jobmap, c->faillist,
-                    c->sublist, c->P0, c->P1, c->P2, c->att0, c->att1, c->phi0, c->ref, c->cprod, c->cnt};
+    cudaDeviceSynchronize();
+    void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
+                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (SideSlot &s : c->side) {
+        void *sp[] = {s.list, s.count, s.P2, s.att1, s.jbest};
+        for (void *p : sp)
+            if (p) cudaFree(p);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    if (c->h_npk) cudaFreeHost(c->h_npk);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->evk0) cudaEventDestroy(c->evk0);
-    if (c->evk1) cudaEventDestroy(c->evk1);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -119,14 +142,10 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     c->np = samples;
     c->stride = (samples + 127) / 128 * 128;
     c->blocks = 4 * (samples / NFFT) - 1;                    // wsprd.c:516
-    c->jobcap = std::max(maxcap, 256);
-    c->failcap = std::max(c->jobcap / 4, 64);
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    CK(cudaEventCreate(&c->evk0));
-    CK(cudaEventCreate(&c->evk1));
-    size_t B = (size_t)maxcap, J = (size_t)c->jobcap, F = (size_t)c->failcap;
+    size_t B = (size_t)maxcap;
     CK(dalloc(&c->I, B * c->stride));
     CK(dalloc(&c->Q, B * c->stride));
     CK(cudaMemset(c->I, 0, B * c->stride * sizeof(float)));
@@ -138,21 +157,35 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(dalloc(&c->spots, B * MAXUNIQ));
     CK(cudaMemset(c->spots, 0, B * MAXUNIQ * sizeof(Spot)));
     CK(dalloc(&c->nres, B));
-    CK(dalloc(&c->jobs, J));
-    CK(dalloc(&c->jobmap, B * MAXCAND));
-    CK(dalloc(&c->faillist, J));
-    CK(dalloc(&c->sublist, B));
-    CK(dalloc(&c->P0, J * MAXLAGS * NSYM));
-    CK(dalloc(&c->P1, J * NFREQ1 * NSYM));
-    CK(dalloc(&c->P2, F * (NJIT - 1) * NSYM));
-    CK(dalloc(&c->att0, J));
-    CK(dalloc(&c->att1, F * (NJIT - 1)));
+    CK(dalloc(&c->jobs, B));
+    CK(dalloc(&c->att0, B));
+    CK(dalloc(&c->ident, B));
+    CK(dalloc(&c->setup_list, B));
+    CK(dalloc(&c->job_list, B));
+    CK(dalloc(&c->res_list, B));
+    CK(dalloc(&c->sub_list, B));
+    CK(dalloc(&c->P0, B * MAXLAGS * NSYM));
+    CK(dalloc(&c->P1, B * NFREQ1 * NSYM));
     CK(dalloc(&c->phi0, B * NSYM));
     CK(dalloc(&c->ref, B * NSIG));
     CK(dalloc(&c->cprod, B * CPAD));
     CK(dalloc(&c->cnt, 1));
     CK(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
-    CK(cudaMallocHost((void **)&c->h_npk, B * sizeof(int)));
+    {
+        std::vector<int> id(B);
+        for (size_t i = 0; i < B; i++) id[i] = (int)i;
+        CK(cudaMemcpy(c->ident, id.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    for (SideSlot &s : c->side) {
+        s.cap = std::max(16, std::min(maxcap, 256));
+        CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CK(dalloc(&s.list, B));
+        CK(dalloc(&s.count, 1));
+        CK(dalloc(&s.P2, (size_t)s.cap * (NJIT - 1) * NSYM));
+        CK(dalloc(&s.att1, (size_t)s.cap * (NJIT - 1)));
+        CK(dalloc(&s.jbest, (size_t)s.cap));
+    }
     HostTables t;
     host_tables(t);
     upload_tables(t);
@@ -203,7 +236,7 @@ extern "C" int wspr_ctx_normalise(wspr_ctx *c) {
     return WSPR_OK;
 }
 
-static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o, int ipass) {
+static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
     DecodeParams p;
     p.np = c->np;
     p.stride = c->stride;
@@ -211,16 +244,15 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o, int
     p.dialfreq = o.freq;
     p.quickmode = o.quickmode;
     p.subtraction = o.subtraction;
-    p.ipass = ipass;
-    p.maxdrift = (ipass == 2) ? 0 : 4;                       // wsprd.c:524-531
-    p.minsync1 = 0.10;
-    p.minsync2 = (ipass == 2) ? 0.10 : 0.12;
+    p.npasses = o.npasses;
+    p.minsync1 = 0.10;                                       // wsprd.c:424-433
     p.symfac = 50;
-    p.minrms = 52.0 * (p.symfac / 64.0);                     // wsprd.c:429
+    p.minrms = 52.0 * (p.symfac / 64.0);
     p.delta = 60;
     p.maxcycles = 10000;
     p.lagstep = o.quickmode ? 16 : 8;                        // wsprd.c:715-717
     p.nlags = 256 / p.lagstep + 1;
+    p.fano_budget = 4096;
     return p;
 }
 
@@ -230,113 +262,112 @@ static int read_counters(wspr_ctx *c) {
     return WSPR_OK;
 }
 
-__global__ void k_begin_pass(CapState *caps, int ncap, int ipass) {
-    int cap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cap >= ncap) return;
-    // wsprd.c:522: no second pass for a capture whose first pass decoded nothing; mark it by an impossible count
-    if (ipass >= 1 && caps[cap].uniques == 0) caps[cap].broken = 2;
-}
-__global__ void k_mask_done(CapState *caps, int ncap) {
-    int cap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cap >= ncap) return;
-    if (caps[cap].uniques == 0) {
-        caps[cap].npk = 0;
+// a side slot whose previous work has completed (waits for the oldest one if all are in flight)
+static int acquire_side(wspr_ctx *c, SideSlot **out) {
+    for (int pass = 0; pass < 2; pass++) {
+        for (SideSlot &s : c->side) {
+            if (s.busy && cudaEventQuery(s.done) == cudaSuccess) s.busy = false;
+            if (!s.busy) {
+                *out = &s;
+                return WSPR_OK;
+            }
+        }
+        CK(cudaEventSynchronize(c->side[0].done));
     }
-}
-__global__ void k_gather_npk(const CapState *caps, int *npk, int ncap) {
-    int cap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cap < ncap) npk[cap] = caps[cap].npk;
+    return fail(WSPR_ERR_CUDA, "no side stream available");
 }
 
-// one wave: candidate ranks [r0, r1) of all captures
-static int run_wave(wspr_ctx *c, const DecodeParams &p, int r0, int r1) {
-    CK(cudaMemsetAsync(c->cnt, 0, sizeof(Counters), c->st));
-    launch_make_jobs(c->cands, c->caps, c->jobs, c->jobmap, c->cnt, c->ncap, r0, r1, c->jobcap, c->st);
-    if (read_counters(c)) return WSPR_ERR_CUDA;
-    int njobs = std::min(c->h_cnt->njobs, c->jobcap);
-    if (njobs == 0) return WSPR_OK;
-    if (c->time_kernels) CK(cudaEventRecord(c->evk0, c->st));
-    launch_sync_lags(c->I, c->Q, c->jobs, njobs, c->P0, p, c->st);
-    if (c->time_kernels) {
-        CK(cudaEventRecord(c->evk1, c->st));
-        CK(cudaEventSynchronize(c->evk1));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
-        c->sync_ms += ms;
-        c->sync_launches += 1;
-        c->sync_cells += (double)njobs * p.nlags * NSYM;
-    }
-    launch_sync_freqs(c->I, c->Q, c->jobs, njobs, c->P1, c->att0, p, c->st);
-    launch_fano(c->att0, njobs, p, c->st);
-    launch_collect_failures(c->jobs, njobs, c->att0, c->faillist, c->cnt, c->st);
-    if (!p.quickmode) {
-        if (read_counters(c)) return WSPR_ERR_CUDA;
-        int nfail = c->h_cnt->nfail;
-        for (int f0 = 0; f0 < nfail; f0 += c->failcap) {
-            int n = std::min(c->failcap, nfail - f0);
-            launch_jitter(c->I, c->Q, c->jobs, c->faillist + f0, n, c->P2, c->att1, p, c->st);
-            launch_fano(c->att1, n * (NJIT - 1), p, c->st);
-            launch_pick_jitter(c->jobs, c->faillist + f0, n, c->att1, c->st);
+static int wait_any_side(wspr_ctx *c) {
+    for (SideSlot &s : c->side)
+        if (s.busy) {
+            CK(cudaEventSynchronize(s.done));
+            s.busy = false;
+            return WSPR_OK;
         }
-    }
-    launch_resolve(c->jobs, c->jobmap, c->cands, c->caps, c->spots, c->sublist, c->cnt, c->ncap, r0, r1, p, c->st);
-    if (p.subtraction && p.ipass == 0) {
-        if (read_counters(c)) return WSPR_ERR_CUDA;
-        int nsub = c->h_cnt->nsub;
-        launch_subtract(c->I, c->Q, c->caps, c->sublist, nsub, c->phi0, c->ref, c->cprod, p, c->st);
-    }
-    CK(cudaGetLastError());
-    return WSPR_OK;
+    return fail(WSPR_ERR_CUDA, "scheduler stalled: captures parked but no side stream is in flight");
 }
 
 extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     if (!c) return fail(WSPR_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     const int ncap = c->ncap;
+    const DecodeParams p = make_params(c, o);
     c->sync_ms = 0.0f;
     c->sync_launches = 0;
     c->sync_cells = 0.0;
+    c->rounds = 0;
+    c->deferred = 0;
+    c->kev_jobs.clear();
+    size_t kev_used = 0;
     CK(cudaEventRecord(c->ev0, c->st));
-    launch_reset_caps(c->caps, ncap, c->st);
-    for (int ipass = 0; ipass < o.npasses && ncap > 0; ipass++) {
-        DecodeParams p = make_params(c, o, ipass);
-        launch_spectrogram(c->I, c->Q, c->psT, ncap, p, c->st);
-        CK(cudaMemsetAsync(c->cnt, 0, sizeof(Counters), c->st));
-        launch_candidates(c->psT, c->cands, c->caps, c->smspec, c->cnt, ncap, p, c->st);
-        if (ipass >= 1) {                                    // wsprd.c:522 (per capture)
-            k_mask_done<<<(ncap + 127) / 128, 128, 0, c->st>>>(c->caps, ncap);
-        }
-        k_gather_npk<<<(ncap + 127) / 128, 128, 0, c->st>>>(c->caps, c->nres, ncap);
-        CK(cudaMemcpyAsync(c->h_npk, c->nres, (size_t)ncap * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        int maxnpk = 0;
-        std::vector<int> hist(MAXCAND + 1, 0);               // hist[r] = captures with more than r candidates
-        for (int i = 0; i < ncap; i++) {
-            maxnpk = std::max(maxnpk, c->h_npk[i]);
-            for (int r = 0; r < c->h_npk[i]; r++) hist[r]++;
-        }
-        if (maxnpk == 0) {
-            if (ipass == 0) break;
+    launch_reset_caps(c->caps, ncap, o.npasses, c->st);
+    while (ncap > 0) {
+        launch_plan(c->caps, c->cands, c->jobs, c->setup_list, c->job_list, c->res_list, c->cnt, ncap, o.npasses, c->st);
+        if (read_counters(c)) return WSPR_ERR_CUDA;
+        const Counters h = *c->h_cnt;
+        if (h.ndone == ncap) break;
+        if (h.nsetup == 0 && h.njobs == 0 && h.nres == 0) {   // everything still open is parked on a side stream
+            if (wait_any_side(c)) return WSPR_ERR_CUDA;
             continue;
         }
-        launch_coarse(c->psT, c->cands, c->caps, ncap, maxnpk, p, c->st);
-        const bool serial = (o.subtraction && ipass == 0);
-        int r0 = 0;
-        while (r0 < maxnpk) {
-            int r1 = r0 + 1;
-            if (!serial) {                                   // as many ranks as fit the job buffers
-                int jobs = hist[r0];
-                while (r1 < maxnpk && jobs + hist[r1] <= c->jobcap) jobs += hist[r1++];
+        c->rounds++;
+        // captures entering a pass: spectrogram, candidate search, coarse sync (wsprd.c:536-678)
+        launch_spectrogram(c->I, c->Q, c->psT, c->setup_list, h.nsetup, p, c->st);
+        launch_candidates(c->psT, c->cands, c->caps, c->smspec, c->setup_list, h.nsetup, p, c->st);
+        launch_coarse(c->psT, c->cands, c->caps, c->setup_list, h.nsetup, p, c->st);
+        // one candidate of every ready capture (wsprd.c:697-766)
+        int nres_max = h.nres;
+        if (h.njobs > 0) {
+            SideSlot *side = nullptr;
+            if (acquire_side(c, &side)) return WSPR_ERR_CUDA;
+            CK(cudaMemsetAsync(side->count, 0, sizeof(int), c->st));
+            if (c->time_kernels) {
+                while (c->kev.size() < kev_used + 2) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    c->kev.push_back(e);
+                }
+                CK(cudaEventRecord(c->kev[kev_used], c->st));
             }
-            int rc = run_wave(c, p, r0, r1);
-            if (rc) return rc;
-            r0 = r1;
+            launch_sync_lags(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, p, c->st);
+            if (c->time_kernels) {
+                CK(cudaEventRecord(c->kev[kev_used + 1], c->st));
+                kev_used += 2;
+                c->kev_jobs.push_back(h.njobs);
+            }
+            launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P1, c->att0, p, c->st);
+            launch_fano_round(c->att0, c->job_list, h.njobs, p, c->st);
+            launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, side->list, side->count, c->cnt, p,
+                           c->st);
+            if (read_counters(c)) return WSPR_ERR_CUDA;
+            const int ndefer = c->h_cnt->ndefer;
+            nres_max = c->h_cnt->nres;
+            if (ndefer > 0) {                                 // finish them off the critical path
+                c->deferred += ndefer;
+                for (int off = 0; off < ndefer; off += side->cap)
+                    launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list, off, std::min(side->cap, ndefer - off),
+                                    side->P2, side->att1, side->jbest, p, side->st);
+                CK(cudaEventRecord(side->done, side->st));
+                side->busy = true;
+            }
         }
+        // in-order tail of the candidate loop for everything that finished, then the subtractions (wsprd.c:768-822)
+        launch_resolve(c->jobs, c->caps, c->spots, c->res_list, nres_max, c->sub_list, c->cnt, p, c->st);
+        if (p.subtraction)
+            launch_subtract(c->I, c->Q, c->caps, c->sub_list, nres_max, c->cnt, c->phi0, c->ref, c->cprod, p, c->st);
+        CK(cudaGetLastError());
     }
     launch_finish(c->caps, c->spots, c->nres, ncap, c->st);
     CK(cudaEventRecord(c->ev1, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    for (size_t k = 0; k + 1 < kev_used; k += 2) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->kev[k], c->kev[k + 1]));
+        c->sync_ms += ms;
+        c->sync_launches += 1;
+        c->sync_cells += (double)c->kev_jobs[k / 2] * p.nlags * NSYM;
+    }
     CK(cudaGetLastError());
     return WSPR_OK;
 }
@@ -346,6 +377,8 @@ extern "C" void *wspr_ctx_stream(wspr_ctx *c) { return c ? (void *)c->st : nullp
 extern "C" float wspr_ctx_last_sync_ms(wspr_ctx *c) { return c ? c->sync_ms : 0.0f; }
 extern "C" int wspr_ctx_last_sync_launches(wspr_ctx *c) { return c ? c->sync_launches : 0; }
 extern "C" double wspr_ctx_last_sync_cells(wspr_ctx *c) { return c ? c->sync_cells : 0.0; }
+extern "C" int wspr_ctx_last_rounds(wspr_ctx *c) { return c ? c->rounds : 0; }
+extern "C" int wspr_ctx_last_deferred(wspr_ctx *c) { return c ? c->deferred : 0; }
 extern "C" int wspr_ctx_time_kernels(wspr_ctx *c, int on) {
     if (!c) return WSPR_ERR_ARG;
     c->time_kernels = on != 0;
@@ -381,8 +414,8 @@ extern "C" int wspr_ctx_spectrogram(wspr_ctx *c, float *ps_out) {
     CK(cudaSetDevice(c->device));
     decoder_options o;
     memset(&o, 0, sizeof o);
-    DecodeParams p = make_params(c, o, 0);
-    launch_spectrogram(c->I, c->Q, c->psT, c->ncap, p, c->st);
+    DecodeParams p = make_params(c, o);
+    launch_spectrogram(c->I, c->Q, c->psT, c->ident, c->ncap, p, c->st);
     float *tmp = nullptr;
     size_t n = (size_t)c->ncap * c->blocks * NFFT;
     CK(dalloc(&tmp, n));
@@ -393,20 +426,28 @@ extern "C" int wspr_ctx_spectrogram(wspr_ctx *c, float *ps_out) {
     return WSPR_OK;
 }
 
+__global__ void k_set_pass(CapState *caps, int ncap, int ipass) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap < ncap) caps[cap].ipass = ipass;
+}
+__global__ void k_gather_npk(const CapState *caps, int *npk, int ncap) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap < ncap) npk[cap] = caps[cap].npk;
+}
+
 extern "C" int wspr_ctx_candidates(wspr_ctx *c, int maxdrift, cand *cands, int *npk, float *smspec) {
     if (!c || !cands || !npk) return fail(WSPR_ERR_ARG, "wspr_ctx_candidates");
     CK(cudaSetDevice(c->device));
     decoder_options o;
     memset(&o, 0, sizeof o);
-    DecodeParams p = make_params(c, o, 0);
-    p.maxdrift = maxdrift;
-    launch_reset_caps(c->caps, c->ncap, c->st);
-    launch_spectrogram(c->I, c->Q, c->psT, c->ncap, p, c->st);
-    CK(cudaMemsetAsync(c->cnt, 0, sizeof(Counters), c->st));
+    DecodeParams p = make_params(c, o);
+    launch_reset_caps(c->caps, c->ncap, 1, c->st);
+    // the coarse search takes its drift range from the pass number: 4 in passes 0/1, 0 in pass 2 (wsprd.c:524-531)
+    k_set_pass<<<(c->ncap + 127) / 128, 128, 0, c->st>>>(c->caps, c->ncap, maxdrift == 0 ? 2 : 0);
+    launch_spectrogram(c->I, c->Q, c->psT, c->ident, c->ncap, p, c->st);
     CK(cudaMemsetAsync(c->cands, 0, (size_t)c->ncap * MAXCAND * sizeof(Cand), c->st));
-    launch_candidates(c->psT, c->cands, c->caps, c->smspec, c->cnt, c->ncap, p, c->st);
-    if (read_counters(c)) return WSPR_ERR_CUDA;
-    launch_coarse(c->psT, c->cands, c->caps, c->ncap, c->h_cnt->maxnpk, p, c->st);
+    launch_candidates(c->psT, c->cands, c->caps, c->smspec, c->ident, c->ncap, p, c->st);
+    launch_coarse(c->psT, c->cands, c->caps, c->ident, c->ncap, p, c->st);
     k_gather_npk<<<(c->ncap + 127) / 128, 128, 0, c->st>>>(c->caps, c->nres, c->ncap);
     CK(cudaMemcpyAsync(npk, c->nres, (size_t)c->ncap * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(cands, c->cands, (size_t)c->ncap * MAXCAND * sizeof(Cand), cudaMemcpyDeviceToHost, c->st));
@@ -557,12 +598,16 @@ extern "C" void subtract_signal2(float *id, float *qd, long np, float f0, int sh
         int zero = 0;
         decoder_options o;
         memset(&o, 0, sizeof o);
-        DecodeParams p = make_params(c, o, 0);
+        DecodeParams p = make_params(c, o);
+        Counters hc;
+        memset(&hc, 0, sizeof hc);
+        hc.nsub = 1;
         cudaError_t e = cudaMemcpyAsync(c->caps, &cs, sizeof cs, cudaMemcpyHostToDevice, c->st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->sublist, &zero, sizeof(int), cudaMemcpyHostToDevice, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->sub_list, &zero, sizeof(int), cudaMemcpyHostToDevice, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->cnt, &hc, sizeof hc, cudaMemcpyHostToDevice, c->st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
         if (e == cudaSuccess) {
-            launch_subtract(c->I, c->Q, c->caps, c->sublist, 1, c->phi0, c->ref, c->cprod, p, c->st);
+            launch_subtract(c->I, c->Q, c->caps, c->sub_list, 1, c->cnt, c->phi0, c->ref, c->cprod, p, c->st);
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) rc = fail(WSPR_ERR_CUDA, "subtract_signal2", e);

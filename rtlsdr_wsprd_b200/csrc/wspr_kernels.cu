@@ -47,9 +47,10 @@ __device__ __forceinline__ double twopidt() { return 2.0 * M_PI * 1.0 / 375.0; }
 // stores and the per-bin block sums of K2 coalesced).
 // =========================================================================================================
 __global__ void __launch_bounds__(256) k_spectrogram(const float *__restrict__ I, const float *__restrict__ Q,
-                                                     float *__restrict__ psT, int stride, int blocks) {
+                                                     float *__restrict__ psT, const int *__restrict__ list, int stride,
+                                                     int blocks) {
     __shared__ double re[NFFT], im[NFFT];
-    const int b = blockIdx.x, cap = blockIdx.y, t = threadIdx.x;
+    const int b = blockIdx.x, cap = list[blockIdx.y], t = threadIdx.x;
     const float *ip = I + (size_t)cap * stride + b * HOP;
     const float *qp = Q + (size_t)cap * stride + b * HOP;
     for (int n = t; n < NFFT; n += 256) {
@@ -82,9 +83,10 @@ __global__ void __launch_bounds__(256) k_spectrogram(const float *__restrict__ I
     }
 }
 
-void launch_spectrogram(const float *I, const float *Q, float *psT, int ncap, const DecodeParams &p, cudaStream_t st) {
-    if (ncap <= 0 || p.blocks <= 0) return;
-    k_spectrogram<<<dim3(p.blocks, ncap), 256, 0, st>>>(I, Q, psT, p.stride, p.blocks);
+void launch_spectrogram(const float *I, const float *Q, float *psT, const int *list, int n, const DecodeParams &p,
+                        cudaStream_t st) {
+    if (n <= 0 || p.blocks <= 0) return;
+    k_spectrogram<<<dim3(p.blocks, n), 256, 0, st>>>(I, Q, psT, list, p.stride, p.blocks);
     LAUNCHED();
 }
 
@@ -94,11 +96,11 @@ void launch_spectrogram(const float *I, const float *Q, float *psT, int ncap, co
 // =========================================================================================================
 __global__ void __launch_bounds__(512) k_candidates(const float *__restrict__ psT, Cand *__restrict__ cands,
                                                     CapState *__restrict__ caps, float *__restrict__ smspec_dbg,
-                                                    Counters *cnt, int blocks) {
+                                                    const int *__restrict__ list, int blocks) {
     __shared__ float psavg[NFFT];
     __shared__ float sm[NSMOOTH];
     __shared__ float noise;
-    const int cap = blockIdx.x, t = threadIdx.x;
+    const int cap = list[blockIdx.x], t = threadIdx.x;
     const float *ps = psT + (size_t)cap * blocks * NFFT;
     float acc = 0.0f;
     for (int b = 0; b < blocks; b++) acc += ps[(size_t)b * NFFT + t];     // block order, :557-561
@@ -155,15 +157,14 @@ __global__ void __launch_bounds__(512) k_candidates(const float *__restrict__ ps
         // so the cap is only reachable on pathological spectra -- count unfiltered maxima to mirror it exactly.
         caps[cap].npk = npk;
         caps[cap].broken = 0;
-        atomicMax(&cnt->maxnpk, npk);
-        atomicAdd(&cnt->totnpk, npk);
+        caps[cap].rank = 0;
     }
 }
 
-void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, Counters *cnt, int ncap,
+void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, const int *list, int n,
                        const DecodeParams &p, cudaStream_t st) {
-    if (ncap <= 0) return;
-    k_candidates<<<ncap, 512, 0, st>>>(psT, cands, caps, smspec_dbg, cnt, p.blocks);
+    if (n <= 0) return;
+    k_candidates<<<n, 512, 0, st>>>(psT, cands, caps, smspec_dbg, list, p.blocks);
     LAUNCHED();
 }
 
@@ -175,12 +176,15 @@ void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *sms
 // three hypotheses evaluated here (with the reference's literal index formula).
 // =========================================================================================================
 constexpr int COARSE_BINS = 12;
+constexpr int COARSE_RANKS = 16;            // grid width; a CTA strides over the ranks of its capture
 __global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, Cand *__restrict__ cands,
-                                                const CapState *__restrict__ caps, int blocks, int maxdrift) {
+                                                const CapState *__restrict__ caps, const int *__restrict__ list, int blocks) {
     extern __shared__ float sq[];           // [blocks][COARSE_BINS] sqrt(ps)
     __shared__ float s_sync[288];
-    const int rank = blockIdx.x, cap = blockIdx.y, t = threadIdx.x;
-    if (rank >= caps[cap].npk) return;
+    const int cap = list[blockIdx.y], t = threadIdx.x;
+    const int npk = caps[cap].npk, maxdrift = pass_maxdrift(caps[cap].ipass);
+  for (int rank = blockIdx.x; rank < npk; rank += COARSE_RANKS) {
+    __syncthreads();                        // the previous rank's tables are no longer in use
     Cand *c = cands + (size_t)cap * MAXCAND + rank;
     const int if0 = (int)((double)c->freq / W_HALF_DF + 256);
     const int lo = if0 - 6;
@@ -235,57 +239,85 @@ __global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, C
             c->sync = best;
         }
     }
+  }
 }
 
-void launch_coarse(const float *psT, Cand *cands, const CapState *caps, int ncap, int maxnpk, const DecodeParams &p,
+// the capture may start its candidate loop (separate tiny kernel: every k_coarse CTA of the capture must be done)
+__global__ void k_setup_done(CapState *__restrict__ caps, const int *__restrict__ list, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) caps[list[i]].phase = PH_READY;
+}
+
+void launch_coarse(const float *psT, Cand *cands, const CapState *caps, const int *list, int n, const DecodeParams &p,
                    cudaStream_t st) {
-    if (ncap <= 0 || maxnpk <= 0) return;
+    if (n <= 0) return;
     size_t smem = (size_t)p.blocks * COARSE_BINS * sizeof(float);
-    k_coarse<<<dim3(maxnpk, ncap), 288, smem, st>>>(psT, cands, caps, p.blocks, p.maxdrift);
+    k_coarse<<<dim3(COARSE_RANKS, n), 288, smem, st>>>(psT, cands, caps, list, p.blocks);
+    LAUNCHED();
+    k_setup_done<<<(n + 127) / 128, 128, 0, st>>>(const_cast<CapState *>(caps), list, n);
     LAUNCHED();
 }
 
 // =========================================================================================================
-// job list for one wave (candidate ranks [r0, r1) of every capture that is still being decoded)
+// round planning: one thread per capture advances its state machine and files it into this round's lists
 // =========================================================================================================
-__global__ void k_make_jobs(const Cand *__restrict__ cands, const CapState *__restrict__ caps, Job *__restrict__ jobs,
-                            int *__restrict__ jobmap, Counters *cnt, int ncap, int r0, int r1, int jobcap) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nr = r1 - r0;
-    if (i >= ncap * nr) return;
-    int cap = i / nr, rank = r0 + i % nr;
-    int slot = -1;
-    if (!caps[cap].broken && rank < caps[cap].npk) {
-        slot = atomicAdd(&cnt->njobs, 1);
-        if (slot < jobcap) {
-            const Cand &c = cands[(size_t)cap * MAXCAND + rank];
-            Job j;
-            j.cap = cap;
-            j.rank = rank;
-            j.freq = c.freq;
-            j.drift = c.drift;
-            j.shift = c.shift;
-            j.sync1 = c.sync;
-            j.snr = c.snr;
-            j.worth = 0;
-            j.fbest = 0;
-            j.decoded = 0;
-            j.idt = 0;
-            j.cycles = 0;
-            for (int k = 0; k < 12; k++) j.dec[k] = 0;
-            jobs[slot] = j;
+__global__ void k_plan(CapState *__restrict__ caps, const Cand *__restrict__ cands, Job *__restrict__ jobs,
+                       int *__restrict__ setup_list, int *__restrict__ job_list, int *__restrict__ res_list, Counters *cnt,
+                       int ncap, int npasses) {
+    int cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= ncap) return;
+    CapState &cs = caps[cap];
+    int phase = *(volatile int *)&cs.phase;              // PH_RESOLVE is set by a side stream while rounds go on
+    if (phase == PH_READY && (cs.rank >= cs.npk || cs.broken)) {
+        // the candidate loop of this pass is over (wsprd.c:697, or one of its breaks :787,:793): next pass, if any.
+        // wsprd.c:521-523: no second pass when the first found nothing.
+        int ip = cs.ipass + 1;
+        if (ip >= npasses || (ip == 1 && cs.uniques == 0)) {
+            phase = PH_DONE;
         } else {
-            slot = -1;
+            phase = PH_SETUP;
+            cs.ipass = ip;
         }
+        cs.phase = phase;
     }
-    jobmap[(size_t)cap * MAXCAND + rank] = slot;
+    if (phase == PH_SETUP) {
+        setup_list[atomicAdd(&cnt->nsetup, 1)] = cap;
+    } else if (phase == PH_READY) {
+        const int slot = atomicAdd(&cnt->njobs, 1);
+        job_list[slot] = cap;
+        const Cand &c = cands[(size_t)cap * MAXCAND + cs.rank];
+        Job j;
+        j.cap = cap;
+        j.rank = cs.rank;
+        j.slot = slot;
+        j.ipass = cs.ipass;
+        j.freq = c.freq;
+        j.drift = c.drift;
+        j.shift = c.shift;
+        j.sync1 = c.sync;
+        j.snr = c.snr;
+        j.worth = 0;
+        j.fbest = 0;
+        j.decoded = 0;
+        j.idt = 0;
+        j.cycles = 0;
+        for (int k = 0; k < 12; k++) j.dec[k] = 0;
+        jobs[cap] = j;
+    } else if (phase == PH_RESOLVE) {
+        __threadfence();                                  // the job record was published before the phase flag
+        res_list[atomicAdd(&cnt->nres, 1)] = cap;
+    } else if (phase == PH_WAIT) {
+        atomicAdd(&cnt->nwait, 1);
+    } else {
+        atomicAdd(&cnt->ndone, 1);
+    }
 }
 
-void launch_make_jobs(const Cand *cands, const CapState *caps, Job *jobs, int *jobmap, Counters *cnt, int ncap, int r0,
-                      int r1, int jobcap, cudaStream_t st) {
-    int n = ncap * (r1 - r0);
-    if (n <= 0) return;
-    k_make_jobs<<<(n + 255) / 256, 256, 0, st>>>(cands, caps, jobs, jobmap, cnt, ncap, r0, r1, jobcap);
+void launch_plan(CapState *caps, const Cand *cands, Job *jobs, int *setup_list, int *job_list, int *res_list, Counters *cnt,
+                 int ncap, int npasses, cudaStream_t st) {
+    if (ncap <= 0) return;
+    cudaMemsetAsync(cnt, 0, sizeof(Counters), st);
+    k_plan<<<(ncap + 127) / 128, 128, 0, st>>>(caps, cands, jobs, setup_list, job_list, res_list, cnt, ncap, npasses);
     LAUNCHED();
 }
 
@@ -360,11 +392,12 @@ constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 225
 constexpr int LAG_THREADS = 32 * (SYMS_PER_CTA + 1);       // 224
 
 __global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
-                                                           const Job *__restrict__ jobs, float4 *__restrict__ P0, int np,
-                                                           int stride, int lagstep, int nlags) {
+                                                           const Job *__restrict__ jobs, const int *__restrict__ job_list,
+                                                           float4 *__restrict__ P0, int np, int stride, int lagstep,
+                                                           int nlags) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float2 win[8 * LAG_PITCH];
-    const Job &job = jobs[blockIdx.x];
+    const Job &job = jobs[job_list[blockIdx.x]];
     const int g = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const float f0 = job.freq, drift = job.drift;
     const int lagmin = job.shift - 128;
@@ -429,10 +462,10 @@ __global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restri
 }
 
 // per-lag sync metric and arg-max over lags (:216-218,227-232); one warp-sized CTA per job
-__global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const float4 *__restrict__ P0, int lagstep,
-                                                 int nlags) {
+__global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const int *__restrict__ job_list,
+                                                 const float4 *__restrict__ P0, int lagstep, int nlags) {
     __shared__ float s_ss[64];
-    Job &job = jobs[blockIdx.x];
+    Job &job = jobs[job_list[blockIdx.x]];
     const int t = threadIdx.x;
     float v = CUDART_NAN_F;
     if (t < nlags) {
@@ -464,13 +497,13 @@ __global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const f
     }
 }
 
-void launch_sync_lags(const float *I, const float *Q, Job *jobs, int njobs, float4 *P0, const DecodeParams &p,
-                      cudaStream_t st) {
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0,
+                      const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, P0, p.np, p.stride, p.lagstep,
-                                                                          p.nlags);
+    k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, job_list, P0, p.np, p.stride,
+                                                                          p.lagstep, p.nlags);
     LAUNCHED();
-    k_pick_lag<<<njobs, 64, 0, st>>>(jobs, P0, p.lagstep, p.nlags);
+    k_pick_lag<<<njobs, 64, 0, st>>>(jobs, job_list, P0, p.lagstep, p.nlags);
     LAUNCHED();
 }
 
@@ -525,10 +558,10 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
 
 // mode 1: five frequencies at the best lag (:722-726)
 __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I, const float *__restrict__ Q,
-                                                    const Job *__restrict__ jobs, float4 *__restrict__ P1, int np,
-                                                    int stride) {
+                                                    const Job *__restrict__ jobs, const int *__restrict__ job_list,
+                                                    float4 *__restrict__ P1, int np, int stride) {
     __shared__ float4 tab[2 * SPS];
-    const Job &job = jobs[blockIdx.x];
+    const Job &job = jobs[job_list[blockIdx.x]];
     const int fi = blockIdx.y, t = threadIdx.x;
     const float fstep = 0.1f;
     const float f0 = job.freq + (float)(fi - 2) * fstep;      // :151
@@ -591,11 +624,14 @@ __device__ float soft_symbols(const float4 *__restrict__ p, unsigned char *sym_o
 
 // arg-max over the five frequencies, the minsync1 gate, and the jitter-0 soft symbols, which are exactly the sums
 // of the winning hypothesis (mode 2 at the same frequency and lag repeats them) -- one thread per job
-__global__ void k_pick_freq(Job *__restrict__ jobs, int njobs, const float4 *__restrict__ P1, Attempt *__restrict__ att,
-                            float minsync1, float minsync2, float minrms, int symfac) {
+__global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_list, int njobs,
+                            const float4 *__restrict__ P1, Attempt *__restrict__ att, float minsync1, float minrms,
+                            int symfac) {
     int jx = blockIdx.x * blockDim.x + threadIdx.x;
     if (jx >= njobs) return;
-    Job &job = jobs[jx];
+    const int cap = job_list[jx];
+    Job &job = jobs[cap];
+    const float minsync2 = pass_minsync2(job.ipass);
     float best = -1e30f, fbest = 0.0f;
     int bf = -1, bshift = 0;
     for (int fi = 0; fi < NFREQ1; fi++) {
@@ -615,11 +651,12 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, int njobs, const float4 *__r
             bshift = job.shift;
         }
     }
-    Attempt &a = att[jx];
-    a.job = jx;
+    Attempt &a = att[cap];
+    a.cap = cap;
     a.idt = 0;
     a.gate = 0;
     a.ok = 0;
+    a.unfinished = 0;
     a.cycles = 0;
     a.sync2 = 0.0f;
     job.freq = fbest;
@@ -635,68 +672,112 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, int njobs, const float4 *__r
     }
 }
 
-void launch_sync_freqs(const float *I, const float *Q, Job *jobs, int njobs, float4 *P1, Attempt *att,
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P1, Attempt *att0,
                        const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, P1, p.np, p.stride);
+    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P1, p.np, p.stride);
     LAUNCHED();
-    k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, njobs, P1, att, p.minsync1, p.minsync2, p.minrms, p.symfac);
+    k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
     LAUNCHED();
 }
 
 // =========================================================================================================
-// K5  Fano decoder, one thread per attempt (fano.c:87-238); metric table in constant memory
+// K5  Fano decoder (fano.c:87-238), metric table in constant memory.
+//   k_fano_round  jitter-0 attempts of a round, one thread per attempt, at most fano_budget cycles: nearly every
+//                 decodable candidate finishes within a few hundred cycles; the rest is re-run by the side stream
+//   k_fano_solo   one attempt per warp (lane 0) -- the latency-optimal shape for the few long runners: a timeout
+//                 is 810 000 strictly sequential cycles, and lanes of one warp on different tree paths would
+//                 serialise each other
 // =========================================================================================================
-__global__ void __launch_bounds__(32) k_fano(Attempt *__restrict__ att, int natt, int delta, unsigned maxcycles) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= natt) return;
-    Attempt &a = att[i];
-    if (!a.gate) return;
+__device__ __forceinline__ void run_fano(Attempt &a, int delta, unsigned maxcycles, unsigned stop_after) {
     unsigned metric, cycles, maxnp;
     unsigned char data[12];
     for (int k = 0; k < 12; k++) data[k] = 0;
-    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles);
+    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles, stop_after);
     a.ok = (rc == 0);
+    a.unfinished = (rc == FANO_STOPPED);
     a.cycles = cycles;
     for (int k = 0; k < 12; k++) a.dec[k] = data[k];
 }
 
-void launch_fano(Attempt *att, int natt, const DecodeParams &p, cudaStream_t st) {
-    if (natt <= 0) return;
-    k_fano<<<(natt + 31) / 32, 32, 0, st>>>(att, natt, p.delta, p.maxcycles);
+__global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, const int *__restrict__ job_list, int njobs,
+                                                   int delta, unsigned maxcycles, unsigned budget) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= njobs) return;
+    Attempt &a = att0[job_list[i]];
+    if (a.gate) run_fano(a, delta, maxcycles, budget);
+}
+
+void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st) {
+    if (njobs <= 0) return;
+    k_fano_round<<<(njobs + 31) / 32, 32, 0, st>>>(att0, job_list, njobs, p.delta, p.maxcycles, p.fano_budget);
     LAUNCHED();
 }
 
-// jobs that were worth a try but did not decode at jitter 0 go on to the jitter search (:741-766)
-__global__ void k_collect_failures(Job *__restrict__ jobs, int njobs, const Attempt *__restrict__ att0,
-                                   int *__restrict__ faillist, Counters *cnt, int quickmode) {
-    int jx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jx >= njobs) return;
-    Job &job = jobs[jx];
-    const Attempt &a = att0[jx];
-    if (a.gate) job.cycles = a.cycles;     // `cycles` keeps the last decoder call's count
+// triage after the jitter-0 attempt: finished candidates go to this round's resolve list; candidates that are worth
+// a try but still undecided (unfinished Fano run, or not decoded and the jitter search is still to come, :741-766)
+// are parked and handed to a side stream.
+__global__ void k_collect(Job *__restrict__ jobs, const Attempt *__restrict__ att0, CapState *__restrict__ caps,
+                          const int *__restrict__ job_list, int njobs, int *__restrict__ res_list,
+                          int *__restrict__ defer_list, int *__restrict__ defer_count, Counters *cnt, int quickmode) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= njobs) return;
+    const int cap = job_list[i];
+    Job &job = jobs[cap];
+    const Attempt &a = att0[cap];
+    bool defer = false;
+    if (a.gate && !a.unfinished) job.cycles = a.cycles;      // `cycles` keeps the last completed decoder call's count
     if (a.gate && a.ok) {
         job.decoded = 1;
         job.idt = 0;
         for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
-    } else if (job.worth && !quickmode) {
-        faillist[atomicAdd(&cnt->nfail, 1)] = jx;
+    } else if (job.worth && (a.unfinished || !quickmode)) {
+        defer = true;
+    }
+    if (defer) {
+        caps[cap].phase = PH_WAIT;
+        defer_list[atomicAdd(defer_count, 1)] = cap;
+        atomicAdd(&cnt->ndefer, 1);
+    } else {
+        res_list[atomicAdd(&cnt->nres, 1)] = cap;
     }
 }
 
-void launch_collect_failures(Job *jobs, int njobs, const Attempt *att0, int *faillist, Counters *cnt, cudaStream_t st) {
+void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
+                    int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_collect_failures<<<(njobs + 127) / 128, 128, 0, st>>>(jobs, njobs, att0, faillist, cnt, 0);
+    k_collect<<<(njobs + 127) / 128, 128, 0, st>>>(jobs, att0, caps, job_list, njobs, res_list, defer_list, defer_count, cnt,
+                                                   p.quickmode);
     LAUNCHED();
 }
 
-// jitter attempts 1..42: shift + 3*(+-1..21) (:742-745), all evaluated at once; the lowest successful idt wins,
+// ---- deferred candidates (side stream) --------------------------------------------------------------------------
+// (1) finish the jitter-0 attempt with the reference's full cycle budget
+__global__ void __launch_bounds__(32) k_fano_solo0(Job *__restrict__ jobs, Attempt *__restrict__ att0,
+                                                   const int *__restrict__ defer_list, int n, int delta, unsigned maxcycles) {
+    if (threadIdx.x != 0 || (int)blockIdx.x >= n) return;
+    const int cap = defer_list[blockIdx.x];
+    Attempt &a = att0[cap];
+    Job &job = jobs[cap];
+    if (a.gate && a.unfinished) {
+        run_fano(a, delta, maxcycles, 0);
+        job.cycles = a.cycles;
+        if (a.ok) {
+            job.decoded = 1;
+            job.idt = 0;
+            for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
+        }
+    }
+}
+
+// (2) jitter attempts 1..42: shift + 3*(+-1..21) (:742-745), all evaluated at once; the lowest successful idt wins,
 // which is what the reference's sequential loop returns.
 __global__ void __launch_bounds__(192) k_jitter(const float *__restrict__ I, const float *__restrict__ Q,
-                                                const Job *__restrict__ jobs, const int *__restrict__ faillist,
+                                                const Job *__restrict__ jobs, const int *__restrict__ defer_list,
                                                 float4 *__restrict__ P2, int np, int stride) {
     __shared__ float4 tab[2 * SPS];
-    const Job &job = jobs[faillist[blockIdx.x]];
+    const Job &job = jobs[defer_list[blockIdx.x]];
+    if (job.decoded) return;                                  // settled by the full-budget jitter-0 run
     const int idt = blockIdx.y + 1, t = threadIdx.x;
     int ii = (idt + 1) / 2;
     if (idt % 2 == 1) ii = -ii;
@@ -710,71 +791,117 @@ __global__ void __launch_bounds__(192) k_jitter(const float *__restrict__ I, con
     P2[((size_t)blockIdx.x * (NJIT - 1) + blockIdx.y) * NSYM + t] =
         correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp);
 }
-__global__ void k_soft_jitter(const float4 *__restrict__ P2, Attempt *__restrict__ att1, const int *__restrict__ faillist,
-                              int natt, float minsync2, float minrms, int symfac) {
+__global__ void k_soft_jitter(const float4 *__restrict__ P2, Attempt *__restrict__ att1, const Job *__restrict__ jobs,
+                              const int *__restrict__ defer_list, int *__restrict__ jbest, int natt, float minrms, int symfac) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= natt) return;
     Attempt &a = att1[i];
-    a.job = faillist[i / (NJIT - 1)];
+    const int e = i / (NJIT - 1);
+    const Job &job = jobs[defer_list[e]];
+    a.cap = job.cap;
     a.idt = i % (NJIT - 1) + 1;
     a.ok = 0;
+    a.unfinished = 0;
     a.cycles = 0;
+    a.gate = 0;
+    if (a.idt == 1) jbest[e] = NJIT;                          // no successful attempt yet
+    if (job.decoded) return;
     float rms;
     float s2 = soft_symbols(P2 + (size_t)i * NSYM, a.sym, &rms, symfac);
     a.sync2 = s2;
-    a.gate = (s2 > minsync2) && (rms > minrms);
+    a.gate = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
 }
 
-void launch_jitter(const float *I, const float *Q, Job *jobs, const int *faillist, int nfail, float4 *P2, Attempt *att1,
-                   const DecodeParams &p, cudaStream_t st) {
-    if (nfail <= 0) return;
-    k_jitter<<<dim3(nfail, NJIT - 1), 192, 0, st>>>(I, Q, jobs, faillist, P2, p.np, p.stride);
-    LAUNCHED();
-    int natt = nfail * (NJIT - 1);
-    k_soft_jitter<<<(natt + 63) / 64, 64, 0, st>>>(P2, att1, faillist, natt, p.minsync2, p.minrms, p.symfac);
-    LAUNCHED();
+// (3) their Fano runs, one per warp.  A run is abandoned as soon as a lower-numbered attempt of the same candidate
+// has succeeded (the sequential loop of the reference would never have reached it).
+struct JitterPoll {
+    const volatile int *best;
+    int idt;
+    __device__ bool operator()(unsigned) const { return *best < idt; }
+};
+__global__ void __launch_bounds__(32) k_fano_jitter(Attempt *__restrict__ att1, int *__restrict__ jbest, int natt, int delta,
+                                                    unsigned maxcycles) {
+    if (threadIdx.x != 0 || (int)blockIdx.x >= natt) return;
+    // attempts are visited jitter-major so that the low-numbered attempts of every candidate start first
+    const int nent = natt / (NJIT - 1);
+    const int e = blockIdx.x % nent, y = blockIdx.x / nent;
+    Attempt &a = att1[(size_t)e * (NJIT - 1) + y];
+    if (!a.gate) return;
+    int *best = jbest + e;
+    if (*(volatile int *)best < a.idt) {
+        a.unfinished = 1;
+        return;
+    }
+    unsigned metric, cycles, maxnp;
+    unsigned char data[12];
+    for (int k = 0; k < 12; k++) data[k] = 0;
+    JitterPoll poll{best, a.idt};
+    int rc = fano_decode<short, JitterPoll>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles, 0, poll);
+    a.ok = (rc == 0);
+    a.unfinished = (rc == FANO_STOPPED);
+    a.cycles = cycles;
+    for (int k = 0; k < 12; k++) a.dec[k] = data[k];
+    if (rc == 0) atomicMin(best, a.idt);
 }
 
-__global__ void k_pick_jitter(Job *__restrict__ jobs, const int *__restrict__ faillist, int nfail,
-                              const Attempt *__restrict__ att1) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nfail) return;
-    Job &job = jobs[faillist[f]];
-    for (int y = 0; y < NJIT - 1; y++) {
-        const Attempt &a = att1[(size_t)f * (NJIT - 1) + y];
-        if (a.gate) job.cycles = a.cycles;
-        if (a.gate && a.ok) {
-            job.decoded = 1;
-            job.idt = a.idt;
-            for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
-            break;
+// (4) winner = lowest successful idt; publish the job and hand the capture back to the rounds
+__global__ void k_pick_jitter(Job *__restrict__ jobs, CapState *__restrict__ caps, const int *__restrict__ defer_list, int n,
+                              const Attempt *__restrict__ att1, int quickmode) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int cap = defer_list[e];
+    Job &job = jobs[cap];
+    if (!job.decoded && !quickmode) {
+        for (int y = 0; y < NJIT - 1; y++) {
+            const Attempt &a = att1[(size_t)e * (NJIT - 1) + y];
+            if (a.gate && !a.unfinished) job.cycles = a.cycles;
+            if (a.gate && a.ok) {
+                job.decoded = 1;
+                job.idt = a.idt;
+                for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
+                break;
+            }
         }
     }
+    __threadfence();
+    *(volatile int *)&caps[cap].phase = PH_RESOLVE;
 }
-void launch_pick_jitter(Job *jobs, const int *faillist, int nfail, const Attempt *att1, cudaStream_t st) {
-    if (nfail <= 0) return;
-    k_pick_jitter<<<(nfail + 63) / 64, 64, 0, st>>>(jobs, faillist, nfail, att1);
+
+// entries [off, off+n) of defer_list; P2/att1/jbest are scratch for n entries
+void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int off,
+                     int n, float4 *P2, Attempt *att1, int *jbest, const DecodeParams &p, cudaStream_t st) {
+    if (n <= 0) return;
+    const int *list = defer_list + off;
+    k_fano_solo0<<<n, 32, 0, st>>>(jobs, att0, list, n, p.delta, p.maxcycles);
+    LAUNCHED();
+    if (!p.quickmode) {
+        const int natt = n * (NJIT - 1);
+        k_jitter<<<dim3(n, NJIT - 1), 192, 0, st>>>(I, Q, jobs, list, P2, p.np, p.stride);
+        LAUNCHED();
+        k_soft_jitter<<<(natt + 63) / 64, 64, 0, st>>>(P2, att1, jobs, list, jbest, natt, p.minrms, p.symfac);
+        LAUNCHED();
+        k_fano_jitter<<<natt, 32, 0, st>>>(att1, jbest, natt, p.delta, p.maxcycles);
+        LAUNCHED();
+    }
+    k_pick_jitter<<<(n + 63) / 64, 64, 0, st>>>(jobs, caps, list, n, att1, p.quickmode);
     LAUNCHED();
 }
 
 // =========================================================================================================
 // resolve: the per-capture, in-order tail of the candidate loop (wsprd.c:768-822): unpack the message, decide on
-// subtraction, apply the two `break`s, drop duplicates, append the spot.  One thread per capture walks the ranks
-// of the wave in order.
+// subtraction, apply the two `break`s, drop duplicates, append the spot.  One thread per capture of the round's
+// resolve list handles that capture's current candidate, then releases the capture for the next round.
 // =========================================================================================================
-__global__ void k_resolve(Job *__restrict__ jobs, const int *__restrict__ jobmap, const Cand *__restrict__ cands,
-                          CapState *__restrict__ caps, Spot *__restrict__ spots, int *__restrict__ sublist,
-                          Counters *cnt, int ncap, int r0, int r1, DecodeParams p) {
-    int cap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cap >= ncap) return;
+__global__ void k_resolve(Job *__restrict__ jobs, CapState *__restrict__ caps, Spot *__restrict__ spots,
+                          const int *__restrict__ res_list, int *__restrict__ sublist, Counters *cnt, DecodeParams p) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cnt->nres) return;
+    const int cap = res_list[e];
     CapState &cs = caps[cap];
     cs.sub_pending = 0;
-    if (cs.broken) return;
     ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP};
-    for (int rank = r0; rank < r1 && rank < cs.npk; rank++) {
-        int jx = jobmap[(size_t)cap * MAXCAND + rank];
-        if (jx < 0) continue;
-        const Job &job = jobs[jx];
+    const Job &job = jobs[cap];
+    for (int once = 0; once < 1; once++) {                    // (the reference's `continue` / `break` targets)
         if (!(job.worth && job.decoded)) continue;
         signed char message[12];
         for (int i = 0; i < 11; i++) message[i] = (signed char)job.dec[i];
@@ -785,7 +912,7 @@ __global__ void k_resolve(Job *__restrict__ jobs, const int *__restrict__ jobmap
         for (int i = 0; i < 7; i++) loc[i] = 0;
         for (int i = 0; i < 3; i++) pwr[i] = 0;
         int noprint = unpack_message(message, hs, call_loc_pow, call, loc, pwr, callsign);
-        if (p.subtraction && p.ipass == 0 && !noprint) {
+        if (p.subtraction && job.ipass == 0 && !noprint) {
             if (channel_symbols(call_loc_pow, hs, cs.chan)) {
                 cs.sub_pending = 1;
                 cs.sub_f0 = job.freq;
@@ -829,12 +956,14 @@ __global__ void k_resolve(Job *__restrict__ jobs, const int *__restrict__ jobmap
         s_copy(r.loc, 7, loc);
         s_copy(r.pwr, 3, pwr);
     }
+    cs.rank = job.rank + 1;
+    cs.phase = PH_READY;
 }
 
-void launch_resolve(Job *jobs, const int *jobmap, const Cand *cands, CapState *caps, Spot *spots, int *sublist,
-                    Counters *cnt, int ncap, int r0, int r1, const DecodeParams &p, cudaStream_t st) {
-    if (ncap <= 0) return;
-    k_resolve<<<(ncap + 31) / 32, 32, 0, st>>>(jobs, jobmap, cands, caps, spots, sublist, cnt, ncap, r0, r1, p);
+void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
+                    const DecodeParams &p, cudaStream_t st) {
+    if (nres_max <= 0) return;
+    k_resolve<<<(nres_max + 31) / 32, 32, 0, st>>>(jobs, caps, spots, res_list, sub_list, cnt, p);
     LAUNCHED();
 }
 
@@ -853,10 +982,10 @@ __device__ __forceinline__ float sub_dphi(float f0, float drift, int i, unsigned
                                 ((double)cs - 1.5) * 375.0 / 256.0));
 }
 
-__global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__restrict__ sublist, int nsub,
+__global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__restrict__ sublist, const Counters *cnt,
                             float *__restrict__ phi0) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nsub) return;
+    if (s >= cnt->nsub) return;
     const CapState &cs = caps[sublist[s]];
     float phi = 0.0f;
     for (int i = 0; i < NSYM; i++) {
@@ -868,10 +997,11 @@ __global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__rest
 
 __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, const float *__restrict__ Q,
                                                  const CapState *__restrict__ caps, const int *__restrict__ sublist,
-                                                 const float *__restrict__ phi0, float2 *__restrict__ ref,
-                                                 float2 *__restrict__ cprod, int np, int stride) {
+                                                 const Counters *cnt, const float *__restrict__ phi0,
+                                                 float2 *__restrict__ ref, float2 *__restrict__ cprod, int np, int stride) {
     __shared__ float s_phi[SPS];
     const int s = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
+    if (s >= cnt->nsub) return;
     const int cap = sublist[s];
     const CapState &cs = caps[cap];
     if (i >= NSYM) {                    // extra CTAs zero the pads of the product buffer
@@ -912,10 +1042,11 @@ constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
 
 __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, float *__restrict__ Q,
                                                          const CapState *__restrict__ caps, const int *__restrict__ sublist,
-                                                         const float2 *__restrict__ ref, const float2 *__restrict__ cprod,
-                                                         int np, int stride) {
+                                                         const Counters *cnt, const float2 *__restrict__ ref,
+                                                         const float2 *__restrict__ cprod, int np, int stride) {
     __shared__ float2 sc[LPF_R * LPF_PITCH];
     const int s = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
+    if (s >= cnt->nsub) return;
     const int cap = sublist[s];
     const CapState &cs = caps[cap];
     const int i0 = tile * LPF_TILE;                          // first output (signal sample index) of the tile
@@ -967,34 +1098,38 @@ __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, 
     }
 }
 
-void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublist, int nsub, float *phi0, float2 *ref,
-                     float2 *cprod, const DecodeParams &p, cudaStream_t st) {
-    if (nsub <= 0) return;
-    k_sub_phase<<<(nsub + 31) / 32, 32, 0, st>>>(caps, sublist, nsub, phi0);
+// grids are sized for nsub_max entries; the actual count is read from cnt->nsub on the device
+void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublist, int nsub_max, const Counters *cnt,
+                     float *phi0, float2 *ref, float2 *cprod, const DecodeParams &p, cudaStream_t st) {
+    if (nsub_max <= 0) return;
+    k_sub_phase<<<(nsub_max + 31) / 32, 32, 0, st>>>(caps, sublist, cnt, phi0);
     LAUNCHED();
-    k_sub_ref<<<dim3(nsub, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, phi0, ref, cprod, p.np, p.stride);
+    k_sub_ref<<<dim3(nsub_max, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
-    k_sub_lpf<<<dim3(nsub, (NSIG + LPF_TILE - 1) / LPF_TILE), LPF_THREADS, 0, st>>>(I, Q, caps, sublist, ref, cprod, p.np,
-                                                                                    p.stride);
+    k_sub_lpf<<<dim3(nsub_max, (NSIG + LPF_TILE - 1) / LPF_TILE), LPF_THREADS, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod,
+                                                                                        p.np, p.stride);
     LAUNCHED();
 }
 
 // =========================================================================================================
 // bookkeeping kernels
 // =========================================================================================================
-__global__ void k_reset_caps(CapState *caps, int ncap) {
+__global__ void k_reset_caps(CapState *caps, int ncap, int npasses) {
     int cap = blockIdx.x * blockDim.x + threadIdx.x;
     if (cap >= ncap) return;
     CapState &cs = caps[cap];
+    cs.phase = npasses > 0 ? PH_SETUP : PH_DONE;
+    cs.ipass = 0;
+    cs.rank = 0;
     cs.npk = 0;
     cs.uniques = 0;
     cs.broken = 0;
     cs.nhash = 0;
     cs.sub_pending = 0;
 }
-void launch_reset_caps(CapState *caps, int ncap, cudaStream_t st) {
+void launch_reset_caps(CapState *caps, int ncap, int npasses, cudaStream_t st) {
     if (ncap <= 0) return;
-    k_reset_caps<<<(ncap + 127) / 128, 128, 0, st>>>(caps, ncap);
+    k_reset_caps<<<(ncap + 127) / 128, 128, 0, st>>>(caps, ncap, npasses);
     LAUNCHED();
 }
 

@@ -40,25 +40,35 @@ struct Spot {
     int cycles;
 };
 
-// decode thresholds and options (wsprd.c:424-433, wsprd.h:44-52)
+// decode thresholds and options (wsprd.c:424-433, wsprd.h:44-52); per-pass values come from pass_maxdrift()/pass_minsync2()
 struct DecodeParams {
     int np;             // samples per capture (45000)
     int stride;         // floats between captures in the I/Q planes
     int blocks;         // spectrogram columns (347)
     int dialfreq;       // options.freq
-    int quickmode, subtraction;
-    int ipass;
-    int maxdrift;       // 4, or 0 in a third pass
-    float minsync1, minsync2, minrms;
+    int quickmode, subtraction, npasses;
+    float minsync1, minrms;
     int symfac, delta;
     unsigned maxcycles;
     int lagstep;        // 8, or 16 in quick mode
     int nlags;          // 33 / 17
+    unsigned fano_budget;   // cycles a jitter-0 Fano attempt may spend inside a round before it is deferred
 };
+// wsprd.c:524-531
+__host__ __device__ inline int pass_maxdrift(int ipass) { return ipass == 2 ? 0 : 4; }
+__host__ __device__ inline float pass_minsync2(int ipass) { return ipass == 2 ? 0.10f : 0.12f; }
 
-// one candidate being refined in the current wave
+// Scheduling.  The reference walks the candidates of one capture strictly in order (a decode is subtracted from the
+// samples before the next candidate is looked at), but captures are independent.  Every capture therefore runs its
+// own little state machine and a *round* advances every capture that is ready by one candidate; a capture whose
+// Fano attempt needs more than fano_budget cycles (or that must go through the 42-attempt jitter search) is parked
+// (PH_WAIT) while a side stream finishes it, and rejoins a later round (PH_RESOLVE) -- it never holds the others up.
+enum Phase { PH_SETUP = 0, PH_READY = 1, PH_WAIT = 2, PH_RESOLVE = 3, PH_DONE = 4 };
+
+// the candidate a capture is currently working on (at most one per capture; indexed by capture)
 struct Job {
-    int cap, rank;
+    int cap, rank, slot; // slot = position in the round's job list (indexes the P0/P1 scratch)
+    int ipass;
     float freq, drift;
     int shift;
     float sync1;        // sync after the frequency search (what the spot reports)
@@ -73,10 +83,11 @@ struct Job {
 
 // one soft-decision attempt (candidate x jitter)
 struct Attempt {
-    int job;
+    int cap;
     int idt;
     int gate;           // sync and rms gates passed -> run the Fano decoder
     int ok;             // decoder result: 1 = decoded
+    int unfinished;     // the attempt ran out of its in-round budget and must be re-run to completion
     unsigned cycles;
     float sync2;
     unsigned char dec[12];
@@ -85,7 +96,10 @@ struct Attempt {
 
 // per-capture bookkeeping across candidates and passes (everything wspr_decode keeps on its stack)
 struct CapState {
+    int phase;          // enum Phase
+    int ipass;          // current pass
     int npk;            // candidates of the current pass
+    int rank;           // next candidate to examine
     int uniques;
     int broken;         // the reference hit one of its `break`s in this pass
     int nhash;
@@ -99,8 +113,7 @@ struct CapState {
 };
 
 struct Counters {
-    int njobs, nfail, nsub, nattempt, maxnpk, totnpk;
-    int pad[2];
+    int nsetup, njobs, nres, ndefer, nsub, nwait, ndone, maxnpk;
 };
 
 // constant tables uploaded once per process (host libm values where the reference computes them with libm)
@@ -113,29 +126,32 @@ struct HostTables {
 };
 void upload_tables(const HostTables &t);
 
-// ---- launchers (all asynchronous on `st`) ----
-void launch_spectrogram(const float *I, const float *Q, float *psT, int ncap, const DecodeParams &p, cudaStream_t st);
-void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, Counters *cnt, int ncap,
+// ---- launchers (all asynchronous on `st`); lists are device arrays of capture indices ----
+void launch_reset_caps(CapState *caps, int ncap, int npasses, cudaStream_t st);
+void launch_plan(CapState *caps, const Cand *cands, Job *jobs, int *setup_list, int *job_list, int *res_list, Counters *cnt,
+                 int ncap, int npasses, cudaStream_t st);
+void launch_spectrogram(const float *I, const float *Q, float *psT, const int *list, int n, const DecodeParams &p,
+                        cudaStream_t st);
+void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *smspec_dbg, const int *list, int n,
                        const DecodeParams &p, cudaStream_t st);
-void launch_coarse(const float *psT, Cand *cands, const CapState *caps, int ncap, int maxnpk, const DecodeParams &p,
+void launch_coarse(const float *psT, Cand *cands, const CapState *caps, const int *list, int n, const DecodeParams &p,
                    cudaStream_t st);
-void launch_make_jobs(const Cand *cands, const CapState *caps, Job *jobs, int *jobmap, Counters *cnt, int ncap, int r0,
-                      int r1, int jobcap, cudaStream_t st);
-void launch_sync_lags(const float *I, const float *Q, Job *jobs, int njobs, float4 *P0, const DecodeParams &p,
-                      cudaStream_t st);
-void launch_sync_freqs(const float *I, const float *Q, Job *jobs, int njobs, float4 *P1, Attempt *att,
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0,
+                      const DecodeParams &p, cudaStream_t st);
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P1, Attempt *att0,
                        const DecodeParams &p, cudaStream_t st);
-void launch_fano(Attempt *att, int natt, const DecodeParams &p, cudaStream_t st);
-void launch_collect_failures(Job *jobs, int njobs, const Attempt *att0, int *faillist, Counters *cnt, cudaStream_t st);
-void launch_jitter(const float *I, const float *Q, Job *jobs, const int *faillist, int nfail, float4 *P2, Attempt *att1,
-                   const DecodeParams &p, cudaStream_t st);
-void launch_pick_jitter(Job *jobs, const int *faillist, int nfail, const Attempt *att1, cudaStream_t st);
-void launch_resolve(Job *jobs, const int *jobmap, const Cand *cands, CapState *caps, Spot *spots, int *sublist,
-                    Counters *cnt, int ncap, int r0, int r1, const DecodeParams &p, cudaStream_t st);
-void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublist, int nsub, float *phi0, float2 *ref,
-                     float2 *cprod, const DecodeParams &p, cudaStream_t st);
+// jitter-0 Fano attempts of the round (budgeted) and their triage into the resolve list / the deferred list
+void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st);
+void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
+                    int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st);
+// side-stream completion of deferred candidates: full-budget jitter-0 Fano, then the jitter search (wsprd.c:741-766)
+void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int off,
+                     int n, float4 *P2, Attempt *att1, int *jbest, const DecodeParams &p, cudaStream_t st);
+void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
+                    const DecodeParams &p, cudaStream_t st);
+void launch_subtract(float *I, float *Q, const CapState *caps, const int *sub_list, int nsub_max, const Counters *cnt,
+                     float *phi0, float2 *ref, float2 *cprod, const DecodeParams &p, cudaStream_t st);
 void launch_finish(CapState *caps, Spot *spots, int *nres, int ncap, cudaStream_t st);
-void launch_reset_caps(CapState *caps, int ncap, cudaStream_t st);
 void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStream_t st);
 
 // stand-alone single-call forms used by the reference-ABI wrappers (sync_and_demodulate / subtract_signal2)

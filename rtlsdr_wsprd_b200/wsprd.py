@@ -101,6 +101,8 @@ def library():
     lib.wspr_ctx_last_decode_ms.restype = C.c_float
     lib.wspr_ctx_last_decode_ms.argtypes = [vp]
     lib.wspr_ctx_time_kernels.argtypes = [vp, C.c_int]
+    lib.wspr_ctx_last_rounds.argtypes = [vp]
+    lib.wspr_ctx_last_deferred.argtypes = [vp]
     lib.wspr_ctx_stream.restype = vp
     lib.wspr_ctx_stream.argtypes = [vp]
     lib.wspr_ctx_last_sync_ms.restype = C.c_float
@@ -250,6 +252,10 @@ class BatchDecoder:
     def stream(self):
         """cudaStream_t (as int) the context issues its work on, e.g. for torch.cuda.ExternalStream."""
         return int(self.lib.wspr_ctx_stream(self.ctx) or 0)
+
+    def schedule_stats(self):
+        """(rounds, deferred candidates) of the last decode."""
+        return int(self.lib.wspr_ctx_last_rounds(self.ctx)), int(self.lib.wspr_ctx_last_deferred(self.ctx))
 
     def time_kernels(self, on=True):
         self.lib.wspr_ctx_time_kernels(self.ctx, int(bool(on)))

@@ -16,4 +16,4 @@ with w.BatchDecoder(n) as d:
         d.upload(I, Q)
         ms = d.decode()
         spots, nres = d.download()
-        print("n", n, "decode ms", round(ms, 2), "captures/s", round(n / ms * 1e3, 1), "spots", int(nres.sum()), "launches", w.kernel_launches(), flush=True)
+        print("n", n, "decode ms", round(ms, 2), "captures/s", round(n / ms * 1e3, 1), "spots", int(nres.sum()), "launches", w.kernel_launches(), "rounds/deferred", d.schedule_stats(), flush=True)
