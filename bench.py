@@ -291,7 +291,8 @@ def run_ours(args):
                 "clocks": clk, "roofline": roofline, "roofline_frontend": frontend,
                 "whole_job_hbm": {"achieved": round(whole_job_gbs, 3), "unit": "GB/s", "frac": round(whole_job_gbs / hbm_peak, 6),
                                   "bytes_per_capture": BYTES_PER_CAPTURE},
-                "cpu_baseline": cpu, "parity": parity, "corpus_gen_s": round(gen_s, 1)}
+                "cpu_baseline": cpu, "parity": parity, "corpus_gen_s": round(gen_s, 1),
+                "schedule": dict(zip(("rounds", "deferred", "settled_f0_jitter_never"), dec.schedule_stats()))}
         print(json.dumps(line), flush=True)
     dec.close()
     if world > 1:

@@ -122,6 +122,9 @@ float wspr_ctx_last_decode_ms(wspr_ctx *ctx);
 /* scheduling statistics of the last decode: rounds driven, candidates finished on side streams */
 int wspr_ctx_last_rounds(wspr_ctx *ctx);
 int wspr_ctx_last_deferred(wspr_ctx *ctx);
+/* how the deferred candidates were settled: out8[0] by the full-budget jitter-0 Fano run, [1] by a jittered attempt,
+ * [2] never decoded */
+int wspr_ctx_last_stats(wspr_ctx *ctx, int *out8);
 /* the cudaStream_t all of the context's copies and kernels are issued on (for callers that record their own events) */
 void *wspr_ctx_stream(wspr_ctx *ctx);
 unsigned long long wspr_kernel_launches(void);
@@ -132,6 +135,14 @@ int wspr_ctx_time_kernels(wspr_ctx *ctx, int on);
 float wspr_ctx_last_sync_ms(wspr_ctx *ctx);
 int wspr_ctx_last_sync_launches(wspr_ctx *ctx);
 double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
+
+/* the Fano decoder kernel (K5) on caller-supplied soft symbols: n vectors of 162 deinterleaved bytes, the batch / device
+ * counterpart of fano() (wsprd/fano.h:14-28; metric table = the one wspr_decode builds, wsprd.c:467-473).  stop_after != 0
+ * cuts a run short after that many cycles (rc 2); solo != 0 runs one attempt per warp (the shape used for long runs).
+ * rc/metric/cycles/maxnp: n entries each, data: n x 12 bytes (host memory); clocks (may be NULL): SM clock ticks each
+ * attempt took. */
+int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
+                    unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks);
 
 /* stage-level access for parity tests (run the first stages of pass 0 on the resident captures) */
 int wspr_ctx_spectrogram(wspr_ctx *ctx, float *ps_out /* [ncaptures][512][blocks], reference layout */);

@@ -121,7 +121,6 @@ int encode(unsigned char *symbols, unsigned char *data, unsigned int nbytes) {
  * final forward move happened exactly on the last allowed cycle, fano.c:234). */
 /* instrumentation for scheduling studies (tools/oracle_stats.py); not part of any result */
 long oracle_stat[16];
-
 int fano(unsigned int *metric, unsigned int *cycles, unsigned int *maxnp, unsigned char *data,
          unsigned char *symbols, unsigned int nbits, int mettab[2][256], int delta, unsigned int maxcycles) {
     enum { MAXN = 256 };
@@ -155,7 +154,9 @@ int fano(unsigned int *metric, unsigned int *cycles, unsigned int *maxnp, unsign
     for (it = 1; it <= limit; it++) {
         if (pos > (int)*maxnp) *maxnp = (unsigned)pos;
         int ng = gam[pos] + tm[pos][sel[pos]];
+        oracle_stat[14]++;
         if (ng >= thr) {                              /* forward, fano.c:158-197 */
+            oracle_stat[15]++;
             if (gam[pos] < thr + delta)
                 while (ng >= thr + delta) thr += delta;
             gam[pos + 1] = ng;
@@ -180,6 +181,7 @@ int fano(unsigned int *metric, unsigned int *cycles, unsigned int *maxnp, unsign
                 break;
             }
             pos--;
+            oracle_stat[13]++;
             if (pos < tail && sel[pos] != 1) {
                 sel[pos]++;
                 enc[pos] ^= 1u;

@@ -69,12 +69,9 @@ struct SideSlot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     bool busy = false;
-    int cap = 0;                   // scratch capacity in candidates
     int *list = nullptr;           // [maxcap] deferred capture indices of one round
     int *count = nullptr;          // device counter of the list
-    float4 *P2 = nullptr;          // [cap][42][162] tone powers of the jitter attempts
-    Attempt *att1 = nullptr;       // [cap][42]
-    int *jbest = nullptr;          // [cap] lowest successful jitter attempt so far
+    ChainScratch *scratch = nullptr;   // [maxcap] attempt results of the parked candidates
 };
 
 struct wspr_ctx {
@@ -95,6 +92,8 @@ struct wspr_ctx {
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
     Counters *h_cnt = nullptr;     // pinned host mirror
+    int *stats = nullptr;          // device [8]: how deferred candidates were settled
+    int h_stats[8] = {0};
     SideSlot side[NSIDE];
     float last_ms = 0.0f, sync_ms = 0.0f;
     int sync_launches = 0, rounds = 0, deferred = 0;
@@ -112,11 +111,11 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
-                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt};
+                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt, c->stats};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (SideSlot &s : c->side) {
-        void *sp[] = {s.list, s.count, s.P2, s.att1, s.jbest};
+        void *sp[] = {s.list, s.count, s.scratch};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (s.done) cudaEventDestroy(s.done);
@@ -170,6 +169,7 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(dalloc(&c->ref, B * NSIG));
     CK(dalloc(&c->cprod, B * CPAD));
     CK(dalloc(&c->cnt, 1));
+    CK(dalloc(&c->stats, 8));
     CK(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
     {
         std::vector<int> id(B);
@@ -177,14 +177,11 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
         CK(cudaMemcpy(c->ident, id.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     }
     for (SideSlot &s : c->side) {
-        s.cap = std::max(16, std::min(maxcap, 256));
         CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CK(dalloc(&s.list, B));
         CK(dalloc(&s.count, 1));
-        CK(dalloc(&s.P2, (size_t)s.cap * (NJIT - 1) * NSYM));
-        CK(dalloc(&s.att1, (size_t)s.cap * (NJIT - 1)));
-        CK(dalloc(&s.jbest, (size_t)s.cap));
+        CK(dalloc(&s.scratch, B));
     }
     HostTables t;
     host_tables(t);
@@ -299,12 +296,22 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     c->deferred = 0;
     c->kev_jobs.clear();
     size_t kev_used = 0;
+    const bool trace = getenv("WSPR_TRACE") != nullptr;
     CK(cudaEventRecord(c->ev0, c->st));
+    CK(cudaMemsetAsync(c->stats, 0, 8 * sizeof(int), c->st));
     launch_reset_caps(c->caps, ncap, o.npasses, c->st);
     while (ncap > 0) {
         launch_plan(c->caps, c->cands, c->jobs, c->setup_list, c->job_list, c->res_list, c->cnt, ncap, o.npasses, c->st);
         if (read_counters(c)) return WSPR_ERR_CUDA;
         const Counters h = *c->h_cnt;
+        if (trace) {
+            float ms = 0;
+            cudaEventRecord(c->ev1, c->st);
+            cudaEventSynchronize(c->ev1);
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            fprintf(stderr, "[wspr] t=%8.2f ms round %3d: setup %5d jobs %5d resolve %5d waiting %5d done %5d\n", ms, c->rounds,
+                    h.nsetup, h.njobs, h.nres, h.nwait, h.ndone);
+        }
         if (h.ndone == ncap) break;
         if (h.nsetup == 0 && h.njobs == 0 && h.nres == 0) {   // everything still open is parked on a side stream
             if (wait_any_side(c)) return WSPR_ERR_CUDA;
@@ -344,9 +351,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             nres_max = c->h_cnt->nres;
             if (ndefer > 0) {                                 // finish them off the critical path
                 c->deferred += ndefer;
-                for (int off = 0; off < ndefer; off += side->cap)
-                    launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list, off, std::min(side->cap, ndefer - off),
-                                    side->P2, side->att1, side->jbest, p, side->st);
+                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list, ndefer, side->scratch, c->stats, p, side->st);
                 CK(cudaEventRecord(side->done, side->st));
                 side->busy = true;
             }
@@ -358,6 +363,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
         CK(cudaGetLastError());
     }
     launch_finish(c->caps, c->spots, c->nres, ncap, c->st);
+    CK(cudaMemcpyAsync(c->h_stats, c->stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(c->ev1, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
@@ -379,6 +385,11 @@ extern "C" int wspr_ctx_last_sync_launches(wspr_ctx *c) { return c ? c->sync_lau
 extern "C" double wspr_ctx_last_sync_cells(wspr_ctx *c) { return c ? c->sync_cells : 0.0; }
 extern "C" int wspr_ctx_last_rounds(wspr_ctx *c) { return c ? c->rounds : 0; }
 extern "C" int wspr_ctx_last_deferred(wspr_ctx *c) { return c ? c->deferred : 0; }
+extern "C" int wspr_ctx_last_stats(wspr_ctx *c, int *out8) {
+    if (!c || !out8) return WSPR_ERR_ARG;
+    for (int i = 0; i < 8; i++) out8[i] = c->h_stats[i];
+    return WSPR_OK;
+}
 extern "C" int wspr_ctx_time_kernels(wspr_ctx *c, int on) {
     if (!c) return WSPR_ERR_ARG;
     c->time_kernels = on != 0;
@@ -506,6 +517,42 @@ extern "C" int wspr_decode(float *idat, float *qdat, int samples, decoder_option
     for (int i = 0; i < n; i++) decodes[i] = tmp[i];
     if (n_results) *n_results = n;
     return 0;
+}
+
+// Fano decoder kernel on caller-supplied soft symbols (n vectors of 162 deinterleaved bytes): the device counterpart
+// of fano() (wsprd/fano.h:14-28) for batches.  solo != 0 selects the one-attempt-per-warp form used for long runs.
+// Outputs are host arrays of n entries (data: n x 12 bytes); returns 0 or a negative error.
+extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo,
+                               int *rc, unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data,
+                               unsigned long long *clocks) {
+    if (n < 0 || !symbols || !rc || !metric || !cycles || !maxnp || !data) return fail(WSPR_ERR_ARG, "wspr_fano_batch");
+    if (n == 0) return WSPR_OK;
+    unsigned char *d_sym = nullptr, *d_data = nullptr;
+    int *d_rc = nullptr;
+    unsigned *d_m = nullptr, *d_c = nullptr, *d_x = nullptr;
+    unsigned long long *d_k = nullptr;
+    int ret = WSPR_OK;
+    cudaError_t e = cudaMalloc((void **)&d_sym, (size_t)n * NSYM);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_data, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_rc, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_m, (size_t)n * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_c, (size_t)n * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_x, (size_t)n * sizeof(unsigned));
+    if (e == cudaSuccess && clocks) e = cudaMalloc((void **)&d_k, (size_t)n * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpy(d_sym, symbols, (size_t)n * NSYM, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_fano_test(d_sym, n, delta, maxcycles, stop_after, solo, d_rc, d_m, d_c, d_x, d_data, d_k, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(rc, d_rc, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(metric, d_m, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cycles, d_c, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(maxnp, d_x, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(data, d_data, (size_t)n * 12, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && clocks) e = cudaMemcpy(clocks, d_k, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) ret = fail(WSPR_ERR_CUDA, "wspr_fano_batch", e);
+    cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k);
+    return ret;
 }
 
 // sync_and_demodulate: correlation grid on the GPU, the handful of scalar reductions on the host in the

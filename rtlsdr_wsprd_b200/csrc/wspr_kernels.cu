@@ -7,6 +7,7 @@
 #include <math_constants.h>
 
 #include "fft512_twiddle.h"
+#include "wspr_fano.cuh"
 #include "wspr_math.cuh"
 #include "wspr_mettab.h"
 
@@ -689,15 +690,13 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
 //                 is 810 000 strictly sequential cycles, and lanes of one warp on different tree paths would
 //                 serialise each other
 // =========================================================================================================
-__device__ __forceinline__ void run_fano(Attempt &a, int delta, unsigned maxcycles, unsigned stop_after) {
-    unsigned metric, cycles, maxnp;
-    unsigned char data[12];
-    for (int k = 0; k < 12; k++) data[k] = 0;
-    int rc = fano_decode<short>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles, stop_after);
-    a.ok = (rc == 0);
-    a.unfinished = (rc == FANO_STOPPED);
-    a.cycles = cycles;
-    for (int k = 0; k < 12; k++) a.dec[k] = data[k];
+__device__ __noinline__ void run_fano(Attempt &a, int delta, unsigned maxcycles, unsigned stop_after, uint4 *node, uint2 *bm) {
+    FanoResult r;
+    fano_fast(r, a.sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), node, bm);
+    a.ok = (r.rc == 0);
+    a.unfinished = (r.rc == FANO_STOPPED);
+    a.cycles = r.cycles;
+    for (int k = 0; k < 12; k++) a.dec[k] = r.data[k];
 }
 
 __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, const int *__restrict__ job_list, int njobs,
@@ -705,7 +704,9 @@ __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, c
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= njobs) return;
     Attempt &a = att0[job_list[i]];
-    if (a.gate) run_fano(a, delta, maxcycles, budget);
+    uint4 node[FANO_NODE_WORDS];                              // every lane decodes: per-thread local arrays
+    uint2 bm[FANO_BM_WORDS];
+    if (a.gate) run_fano(a, delta, maxcycles, budget, node, bm);
 }
 
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st) {
@@ -752,138 +753,176 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 }
 
 // ---- deferred candidates (side stream) --------------------------------------------------------------------------
-// (1) finish the jitter-0 attempt with the reference's full cycle budget
-__global__ void __launch_bounds__(32) k_fano_solo0(Job *__restrict__ jobs, Attempt *__restrict__ att0,
-                                                   const int *__restrict__ defer_list, int n, int delta, unsigned maxcycles) {
-    if (threadIdx.x != 0 || (int)blockIdx.x >= n) return;
-    const int cap = defer_list[blockIdx.x];
-    Attempt &a = att0[cap];
-    Job &job = jobs[cap];
-    if (a.gate && a.unfinished) {
-        run_fano(a, delta, maxcycles, 0);
-        job.cycles = a.cycles;
-        if (a.ok) {
-            job.decoded = 1;
-            job.idt = 0;
-            for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
-        }
-    }
-}
-
-// (2) jitter attempts 1..42: shift + 3*(+-1..21) (:742-745), all evaluated at once; the lowest successful idt wins,
-// which is what the reference's sequential loop returns.
-__global__ void __launch_bounds__(192) k_jitter(const float *__restrict__ I, const float *__restrict__ Q,
-                                                const Job *__restrict__ jobs, const int *__restrict__ defer_list,
-                                                float4 *__restrict__ P2, int np, int stride) {
-    __shared__ float4 tab[2 * SPS];
-    const Job &job = jobs[defer_list[blockIdx.x]];
-    if (job.decoded) return;                                  // settled by the full-budget jitter-0 run
-    const int idt = blockIdx.y + 1, t = threadIdx.x;
-    int ii = (idt + 1) / 2;
-    if (idt % 2 == 1) ii = -ii;
-    ii = 3 * ii;
-    const bool shared_tab = (job.drift == 0.0f);
-    if (shared_tab) build_tables(job.freq, tab, t);
-    __syncthreads();
-    if (t >= NSYM) return;
-    const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
-    float fp = shared_tab ? job.freq : symbol_freq(job.freq, job.drift, t);
-    P2[((size_t)blockIdx.x * (NJIT - 1) + blockIdx.y) * NSYM + t] =
-        correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp);
-}
-__global__ void k_soft_jitter(const float4 *__restrict__ P2, Attempt *__restrict__ att1, const Job *__restrict__ jobs,
-                              const int *__restrict__ defer_list, int *__restrict__ jbest, int natt, float minrms, int symfac) {
+// CHAIN_CTAS small CTAs own one parked candidate and run what is left of its jitter loop (wsprd.c:741-766) with every attempt in
+// flight at once -- attempt 0 is the unfinished jitter-0 Fano run (now with the reference's full cycle budget),
+// attempts 1..42 are the jittered ones, shift + 3*(+-1..21):
+//   (1) the jittered soft-symbol vectors of this CTA's attempts (a few warps per SM keeps every Fano lane at full speed);
+//   (2) lane 0 of one warp per attempt runs the latency-tuned Fano decoder; an attempt is abandoned as soon as a
+//       lower-numbered one has succeeded -- the reference's sequential loop would never have reached it;
+//   (3) the CTA that finishes last picks the winner = lowest successful attempt, exactly what the sequential loop
+//       returns, and hands the capture back to the rounds.  No barrier with other parked candidates anywhere.
+// stats: [0] settled by the full-budget jitter-0 run, [1] by a jittered attempt, [2] never decoded
+__global__ void k_chain_reset(ChainScratch *scratch, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= natt) return;
-    Attempt &a = att1[i];
-    const int e = i / (NJIT - 1);
-    const Job &job = jobs[defer_list[e]];
-    a.cap = job.cap;
-    a.idt = i % (NJIT - 1) + 1;
-    a.ok = 0;
-    a.unfinished = 0;
-    a.cycles = 0;
-    a.gate = 0;
-    if (a.idt == 1) jbest[e] = NJIT;                          // no successful attempt yet
-    if (job.decoded) return;
-    float rms;
-    float s2 = soft_symbols(P2 + (size_t)i * NSYM, a.sym, &rms, symfac);
-    a.sync2 = s2;
-    a.gate = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
+    if (i < n) scratch[i].done = 0;
 }
 
-// (3) their Fano runs, one per warp.  A run is abandoned as soon as a lower-numbered attempt of the same candidate
-// has succeeded (the sequential loop of the reference would never have reached it).
+constexpr int CHAIN_WARPS = 8;                                  // attempts per CTA; ceil(43/8) = 6 CTAs share a candidate
+constexpr int CHAIN_THREADS = CHAIN_WARPS * 32;
+constexpr int CHAIN_GROUP = 1;                                  // jitter attempts correlated per sweep (162 <= 256)
+constexpr int CHAIN_CTAS = (NJIT + CHAIN_WARPS - 1) / CHAIN_WARPS;
+
 struct JitterPoll {
     const volatile int *best;
     int idt;
     __device__ bool operator()(unsigned) const { return *best < idt; }
 };
-__global__ void __launch_bounds__(32) k_fano_jitter(Attempt *__restrict__ att1, int *__restrict__ jbest, int natt, int delta,
-                                                    unsigned maxcycles) {
-    if (threadIdx.x != 0 || (int)blockIdx.x >= natt) return;
-    // attempts are visited jitter-major so that the low-numbered attempts of every candidate start first
-    const int nent = natt / (NJIT - 1);
-    const int e = blockIdx.x % nent, y = blockIdx.x / nent;
-    Attempt &a = att1[(size_t)e * (NJIT - 1) + y];
-    if (!a.gate) return;
-    int *best = jbest + e;
-    if (*(volatile int *)best < a.idt) {
-        a.unfinished = 1;
-        return;
-    }
-    unsigned metric, cycles, maxnp;
-    unsigned char data[12];
-    for (int k = 0; k < 12; k++) data[k] = 0;
-    JitterPoll poll{best, a.idt};
-    int rc = fano_decode<short, JitterPoll>(&metric, &cycles, &maxnp, data, a.sym, NBITS, &c_mettab[0][0], delta, maxcycles, 0, poll);
-    a.ok = (rc == 0);
-    a.unfinished = (rc == FANO_STOPPED);
-    a.cycles = cycles;
-    for (int k = 0; k < 12; k++) a.dec[k] = data[k];
-    if (rc == 0) atomicMin(best, a.idt);
-}
 
-// (4) winner = lowest successful idt; publish the job and hand the capture back to the rounds
-__global__ void k_pick_jitter(Job *__restrict__ jobs, CapState *__restrict__ caps, const int *__restrict__ defer_list, int n,
-                              const Attempt *__restrict__ att1, int quickmode) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
+struct ChainShared {
+    float4 tab[2 * SPS];
+    float4 P[CHAIN_GROUP * NSYM];
+    FanoSharedState fano[CHAIN_WARPS];
+    unsigned char sym[CHAIN_WARPS][NSYM + 2];
+    int gate[CHAIN_WARPS];
+};
+
+__global__ void __launch_bounds__(CHAIN_THREADS) k_defer_chain(const float *__restrict__ I, const float *__restrict__ Q,
+                                                               Job *__restrict__ jobs, const Attempt *__restrict__ att0,
+                                                               CapState *__restrict__ caps, const int *__restrict__ defer_list,
+                                                               ChainScratch *__restrict__ scratch, int np, int stride,
+                                                               float minrms, int symfac, int delta, unsigned maxcycles,
+                                                               int *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    ChainShared &sh = *reinterpret_cast<ChainShared *>(chain_smem);
+    const int e = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int cap = defer_list[e];
     Job &job = jobs[cap];
-    if (!job.decoded && !quickmode) {
-        for (int y = 0; y < NJIT - 1; y++) {
-            const Attempt &a = att1[(size_t)e * (NJIT - 1) + y];
-            if (a.gate && !a.unfinished) job.cycles = a.cycles;
-            if (a.gate && a.ok) {
-                job.decoded = 1;
-                job.idt = a.idt;
-                for (int k = 0; k < 12; k++) job.dec[k] = a.dec[k];
-                break;
+    ChainScratch &cs = scratch[e];
+    const int a_first = blockIdx.y * CHAIN_WARPS;              // attempts [a_first, a_first + CHAIN_WARPS) ∩ [0, NJIT)
+    const float f0 = job.freq, drift = job.drift;
+    const int shift = job.shift;
+    const bool shared_tab = (drift == 0.0f);
+    const float minsync2 = pass_minsync2(job.ipass);
+    const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
+    if (t < CHAIN_WARPS) sh.gate[t] = 0;
+    if (shared_tab && gridDim.y > 1) build_tables(f0, sh.tab, t);
+    __syncthreads();
+    if (a_first == 0) {                                        // attempt 0: the parked jitter-0 soft symbols
+        const Attempt &a = att0[cap];
+        for (int i = t; i < NSYM; i += CHAIN_THREADS) sh.sym[0][i] = a.sym[i];
+        if (t == 0) sh.gate[0] = a.gate && a.unfinished;
+    }
+    if (gridDim.y > 1) {                                       // (quick mode has no jittered attempts: one CTA, attempt 0 only)
+        const int j_first = max(a_first, 1), j_end = min(a_first + CHAIN_WARPS, NJIT);
+        for (int a0i = j_first; a0i < j_end; a0i += CHAIN_GROUP) {
+            const int g = t / NSYM, sym = t - g * NSYM, idt = a0i + g;
+            if (g < CHAIN_GROUP && idt < j_end) {
+                int ii = (idt + 1) / 2;
+                if (idt % 2 == 1) ii = -ii;
+                ii = 3 * ii;
+                const float fp = shared_tab ? f0 : symbol_freq(f0, drift, sym);
+                sh.P[g * NSYM + sym] = correlate_symbol(ip, qp, np, shift + ii + sym * SPS, shared_tab, sh.tab, fp);
+            }
+            __syncthreads();
+            if (t < CHAIN_GROUP && a0i + t < j_end) {
+                float rms;
+                const int al = a0i + t - a_first;
+                const float s2 = soft_symbols(sh.P + t * NSYM, sh.sym[al], &rms, symfac);
+                sh.gate[al] = (s2 > minsync2) && (rms > minrms);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    {
+        const int idt = a_first + warp;
+        const bool run = idt < NJIT && sh.gate[warp];
+        if (lane == 0 && idt < NJIT) {
+            cs.gate[idt] = run;
+            cs.ok[idt] = 0;
+            cs.unfinished[idt] = 0;
+        }
+        if (run && lane == 0) {
+            FanoResult r;
+            JitterPoll poll{&cs.best, idt};
+            fano_shared(r, sh.sym[warp], &c_mettab[0][0], delta, maxcycles, 0, poll, sh.fano[warp]);
+            {
+                cs.ok[idt] = (r.rc == 0);
+                cs.unfinished[idt] = (r.rc == FANO_STOPPED);
+                cs.cycles[idt] = r.cycles;
+                for (int k = 0; k < 12; k++) cs.dec[idt][k] = r.data[k];
+                if (r.rc == 0) atomicMin(&cs.best, idt);
             }
         }
     }
-    __threadfence();
-    *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        const int arrived = atomicAdd(&cs.done, 1);
+        if (arrived == (int)gridDim.y - 1) {                   // the other CTA's results are complete and visible
+            __threadfence();
+            const int nat = (gridDim.y > 1) ? NJIT : 1;
+            const volatile ChainScratch &v = cs;
+            for (int idt = 0; idt < nat; idt++) {
+                if (v.gate[idt] && !v.unfinished[idt]) job.cycles = v.cycles[idt];
+                if (v.gate[idt] && v.ok[idt]) {
+                    job.decoded = 1;
+                    job.idt = idt;
+                    for (int k = 0; k < 12; k++) job.dec[k] = v.dec[idt][k];
+                    break;
+                }
+            }
+            atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
+            __threadfence();
+            *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+        }
+    }
 }
 
-// entries [off, off+n) of defer_list; P2/att1/jbest are scratch for n entries
-void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int off,
-                     int n, float4 *P2, Attempt *att1, int *jbest, const DecodeParams &p, cudaStream_t st) {
+void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
+                     ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st) {
     if (n <= 0) return;
-    const int *list = defer_list + off;
-    k_fano_solo0<<<n, 32, 0, st>>>(jobs, att0, list, n, p.delta, p.maxcycles);
-    LAUNCHED();
-    if (!p.quickmode) {
-        const int natt = n * (NJIT - 1);
-        k_jitter<<<dim3(n, NJIT - 1), 192, 0, st>>>(I, Q, jobs, list, P2, p.np, p.stride);
-        LAUNCHED();
-        k_soft_jitter<<<(natt + 63) / 64, 64, 0, st>>>(P2, att1, jobs, list, jbest, natt, p.minrms, p.symfac);
-        LAUNCHED();
-        k_fano_jitter<<<natt, 32, 0, st>>>(att1, jbest, natt, p.delta, p.maxcycles);
-        LAUNCHED();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_defer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
+        attr_set = true;
     }
-    k_pick_jitter<<<(n + 63) / 64, 64, 0, st>>>(jobs, caps, list, n, att1, p.quickmode);
+    cudaMemsetAsync(scratch, 0x7f, (size_t)n * sizeof(ChainScratch), st);     // best = "no attempt has succeeded"
+    k_chain_reset<<<(n + 127) / 128, 128, 0, st>>>(scratch, n);
+    LAUNCHED();
+    k_defer_chain<<<dim3(n, p.quickmode ? 1 : CHAIN_CTAS), CHAIN_THREADS, sizeof(ChainShared), st>>>(
+        I, Q, jobs, att0, caps, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac, p.delta, p.maxcycles, stats);
+    LAUNCHED();
+}
+
+// stand-alone Fano batches for the C-ABI test hook wspr_fano_batch(): both storage variants of fano_fast
+__global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restrict__ symbols, int n, int delta,
+                                                  unsigned maxcycles, unsigned stop_after, int solo, int *__restrict__ rc,
+                                                  unsigned *__restrict__ metric, unsigned *__restrict__ cycles,
+                                                  unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
+                                                  unsigned long long *__restrict__ clocks) {
+    __shared__ FanoSharedState s_state;
+    uint4 l_node[FANO_NODE_WORDS];
+    uint2 l_bm[FANO_BM_WORDS];
+    const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n || (solo && threadIdx.x != 0)) return;
+    FanoResult r;
+    const long long t0 = clock64();
+    if (solo) fano_shared(r, symbols + (size_t)i * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), s_state);
+    else fano_fast(r, symbols + (size_t)i * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), l_node, l_bm);
+    if (clocks) clocks[i] = (unsigned long long)(clock64() - t0);
+    rc[i] = r.rc;
+    metric[i] = r.metric;
+    cycles[i] = r.cycles;
+    maxnp[i] = r.maxnp;
+    for (int k = 0; k < 12; k++) data[(size_t)i * 12 + k] = r.data[k];
+}
+void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
+                      unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
+                      cudaStream_t st) {
+    if (n <= 0) return;
+    k_fano_test<<<solo ? n : (n + 31) / 32, 32, 0, st>>>(symbols, n, delta, maxcycles, stop_after, solo, rc, metric, cycles, maxnp,
+                                                         data, clocks);
     LAUNCHED();
 }
 

@@ -112,6 +112,15 @@ struct CapState {
     unsigned char chan[NSYM + 2];
 };
 
+// results of the 43 attempts of one parked candidate, shared by the two CTAs that work on it
+struct ChainScratch {
+    int best;           // lowest attempt number that has decoded so far
+    int done;           // CTAs that have finished
+    int gate[NJIT], ok[NJIT], unfinished[NJIT];
+    unsigned cycles[NJIT];
+    unsigned char dec[NJIT][12];
+};
+
 struct Counters {
     int nsetup, njobs, nres, ndefer, nsub, nwait, ndone, maxnpk;
 };
@@ -145,8 +154,8 @@ void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const Deco
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
                     int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st);
 // side-stream completion of deferred candidates: full-budget jitter-0 Fano, then the jitter search (wsprd.c:741-766)
-void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int off,
-                     int n, float4 *P2, Attempt *att1, int *jbest, const DecodeParams &p, cudaStream_t st);
+void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
+                     ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st);
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
                     const DecodeParams &p, cudaStream_t st);
 void launch_subtract(float *I, float *Q, const CapState *caps, const int *sub_list, int nsub_max, const Counters *cnt,
@@ -157,6 +166,10 @@ void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStrea
 // stand-alone single-call forms used by the reference-ABI wrappers (sync_and_demodulate / subtract_signal2)
 void launch_sync_generic(const float *I, const float *Q, int np, float freq, int ifmin, int ifmax, float fstep, int lagmin,
                          int lagmax, int lagstep, float drift, float4 *P, cudaStream_t st);
+
+void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
+                      unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
+                      cudaStream_t st);
 
 // front end (rtlsdr_wsprd.c:126-244)
 void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, uint2 *vals,

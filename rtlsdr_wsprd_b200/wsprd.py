@@ -103,6 +103,7 @@ def library():
     lib.wspr_ctx_time_kernels.argtypes = [vp, C.c_int]
     lib.wspr_ctx_last_rounds.argtypes = [vp]
     lib.wspr_ctx_last_deferred.argtypes = [vp]
+    lib.wspr_ctx_last_stats.argtypes = [vp, vp]
     lib.wspr_ctx_stream.restype = vp
     lib.wspr_ctx_stream.argtypes = [vp]
     lib.wspr_ctx_last_sync_ms.restype = C.c_float
@@ -113,6 +114,7 @@ def library():
     lib.wspr_kernel_launches.restype = C.c_ulonglong
     lib.wspr_ctx_spectrogram.argtypes = [vp, vp]
     lib.wspr_ctx_candidates.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.wspr_fano_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.wspr_decimate_batch.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_int, C.c_int]
     lib.wspr_decimate_device.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.wspr_decimate_last_ms.restype = C.c_float
@@ -255,7 +257,9 @@ class BatchDecoder:
 
     def schedule_stats(self):
         """(rounds, deferred candidates) of the last decode."""
-        return int(self.lib.wspr_ctx_last_rounds(self.ctx)), int(self.lib.wspr_ctx_last_deferred(self.ctx))
+        st = (C.c_int * 8)()
+        self.lib.wspr_ctx_last_stats(self.ctx, st)
+        return int(self.lib.wspr_ctx_last_rounds(self.ctx)), int(self.lib.wspr_ctx_last_deferred(self.ctx)), list(st)[:3]
 
     def time_kernels(self, on=True):
         self.lib.wspr_ctx_time_kernels(self.ctx, int(bool(on)))
@@ -278,6 +282,19 @@ def decode_batch(I, Q, options=None, device=-1):
     _check(lib.wspr_decode_batch(I.ctypes.data, Q.ctypes.data, ncap, samples, options or default_options(),
                                  spots.ctypes.data, n.ctypes.data, int(device)), "wspr_decode_batch")
     return [spots[c, : n[c]].copy() for c in range(ncap)]
+
+
+def fano_batch(symbols, delta=60, maxcycles=10000, stop_after=0, solo=False):
+    """The Fano kernel (K5) on soft symbols uint8[n, 162] (deinterleaved).  Returns dict(rc, metric, cycles, maxnp, data[n,12])."""
+    sym = np.ascontiguousarray(symbols, dtype=np.uint8).reshape(-1, 162)
+    n = sym.shape[0]
+    out = dict(rc=np.zeros(n, np.int32), metric=np.zeros(n, np.uint32), cycles=np.zeros(n, np.uint32),
+               maxnp=np.zeros(n, np.uint32), data=np.zeros((n, 12), np.uint8), clocks=np.zeros(n, np.uint64))
+    _check(library().wspr_fano_batch(sym.ctypes.data, n, int(delta), int(maxcycles), int(stop_after), int(solo),
+                                     out["rc"].ctypes.data, out["metric"].ctypes.data, out["cycles"].ctypes.data,
+                                     out["maxnp"].ctypes.data, out["data"].ctypes.data, out["clocks"].ctypes.data),
+           "wspr_fano_batch")
+    return out
 
 
 def decimate_batch(raw, n_iq=None, max_out=NSAMP, device=-1):

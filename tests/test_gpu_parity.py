@@ -257,6 +257,51 @@ def test_subtract_signal2_abi_against_reference_golden():
         assert np.array_equal(ia, st["sub_%d_i" % dft]) and np.array_equal(qa, st["sub_%d_q" % dft])
 
 
+def test_fano_kernel_against_oracle_random_vectors():
+    """K5 alone: random soft-symbol vectors from clean to hopeless, both storage variants of the device decoder, against
+    fano() of the oracle (return code, metric, cycle count, deepest node, decoded bytes); timeouts at a reduced maxcycles
+    keep the CPU side fast, plus a few at the reference's full 10000."""
+    orc = po.oracle()
+    mettab = ((C.c_int * 256) * 2)()
+    orc.oracle_mettab(mettab)
+    rng = np.random.default_rng(42)
+    msgs = ["K1JT FN20 20", "VA2GKA FN35 37", "G4JNT IO90 60", "<K1ABC> FN42AX 10", "PJ4/K1ABC 37"]
+    vecs = []
+    for k in range(192):
+        sym = H.channel_symbols(msgs[k % len(msgs)])
+        base = np.where(sym >> 1, 128.0 + 50.0, 128.0 - 50.0)
+        sigma = [10, 40, 60, 70, 80, 90, 110, 300][k % 8]
+        soft = np.clip(base + rng.standard_normal(162) * sigma, 0, 255).astype(np.uint8)
+        orc.deinterleave(soft.ctypes.data_as(UP))
+        vecs.append(soft)
+    vecs = np.stack(vecs)
+
+    def oracle_fano(v, maxcycles):
+        met, cyc, mx = C.c_uint(), C.c_uint(), C.c_uint()
+        data = (C.c_ubyte * 12)()
+        s = v.copy()
+        rc = orc.fano(C.byref(met), C.byref(cyc), C.byref(mx), data, s.ctypes.data_as(UP), 81, mettab, 60, maxcycles)
+        return rc, met.value, cyc.value, mx.value, bytes(data)[:10]
+
+    for maxcycles, subset in ((300, vecs), (10000, vecs[:24])):
+        want = [oracle_fano(v, maxcycles) for v in subset]
+        assert any(x[0] == 0 for x in want) and any(x[0] != 0 for x in want)
+        for solo in (0, 1):             # every lane decodes, local state / one lane per warp, shared-memory state
+            got = w.fano_batch(subset, maxcycles=maxcycles, solo=solo)
+            for k, x in enumerate(want):
+                assert (got["rc"][k], got["metric"][k], got["cycles"][k], got["maxnp"][k]) == x[:4], (maxcycles, solo, k)
+                if x[0] == 0:
+                    assert bytes(got["data"][k][:10]) == x[4]
+    # a budgeted run either finishes with the same answer or reports FANO_STOPPED (2) -- never a different answer
+    got = w.fano_batch(vecs, maxcycles=10000, stop_after=2048)
+    full = w.fano_batch(vecs, maxcycles=10000)
+    for k in range(len(vecs)):
+        if got["rc"][k] == 2:
+            assert full["cycles"][k] > 2048
+        else:
+            assert (got["rc"][k], got["cycles"][k], bytes(got["data"][k])) == (full["rc"][k], full["cycles"][k], bytes(full["data"][k]))
+
+
 # ---- front end ----------------------------------------------------------------------------------------------------
 def oracle_decimate(raw, n_iq, max_out):
     orc = po.oracle()

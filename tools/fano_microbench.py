@@ -1,0 +1,18 @@
+"""Latency of one Fano timeout (810 000 cycles) on the GPU: per-thread (0), one lane + shared state (1), warp-cooperative (2)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import rtlsdr_wsprd_b200 as w
+rng = np.random.default_rng(0)
+base = rng.integers(0, 256, size=(4096, 162), dtype=np.uint8)
+for solo in (1, 0):
+    for n in (1, 1, 8, 148, 1024, 4736, 9472):
+        v = base[:n]
+        t0 = time.perf_counter()
+        r = w.fano_batch(v, maxcycles=10000, solo=solo)
+        dt = time.perf_counter() - t0
+        clk = r["clocks"].astype(np.float64)
+        print("mode=%d n=%5d: %7.1f ms wall (timeouts %d); SM clocks per Fano cycle: median %.1f max %.1f -> %.1f ms at 1965 MHz; %.1f Mcycles/s aggregate"
+              % (solo, n, dt * 1e3, int((r["rc"] == -1).sum()), np.median(clk) / 810000, clk.max() / 810000,
+                 clk.max() / 1.965e6, n * 0.81 / dt), flush=True)
