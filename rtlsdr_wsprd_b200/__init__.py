@@ -6,11 +6,11 @@ argument meaning, and the batch / device-resident context a throughput caller us
 every compute call raises ``WsprCudaError`` when the library or a CUDA device is missing.
 """
 from .wsprd import (DecoderOptions, DecoderResults, RESULT_DTYPE, CAND_DTYPE, MAX_UNIQUES, NSAMP, WsprCudaError,
-                    default_options, library, library_path, wspr_decode, decode_batch, BatchDecoder, decimate_batch,
+                    default_options, library, library_path, wspr_decode, decode_batch, BatchDecoder, PipelinedDecoder, decimate_batch,
                     decimate_device, fano_batch, spot_line, read_iq_file, read_c2_file, write_iq_file, normalise_half,
                     kernel_launches, build_library)
 
 __all__ = ["DecoderOptions", "DecoderResults", "RESULT_DTYPE", "CAND_DTYPE", "MAX_UNIQUES", "NSAMP", "WsprCudaError",
-           "default_options", "library", "library_path", "wspr_decode", "decode_batch", "BatchDecoder",
+           "default_options", "library", "library_path", "wspr_decode", "decode_batch", "BatchDecoder", "PipelinedDecoder",
            "decimate_batch", "decimate_device", "fano_batch", "spot_line", "read_iq_file", "read_c2_file", "write_iq_file",
            "normalise_half", "kernel_launches", "build_library"]

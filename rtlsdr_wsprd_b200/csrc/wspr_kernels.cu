@@ -6,6 +6,8 @@
 
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "fft512_twiddle.h"
 #include "wspr_fano.cuh"
 #include "wspr_math.cuh"
@@ -13,10 +15,10 @@
 
 namespace wspr {
 
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};   // contexts may be driven from several host threads
 extern unsigned long long g_frontend_launches;   // wspr_frontend.cu
-unsigned long long kernel_launch_count() { return g_launches + g_frontend_launches; }
-#define LAUNCHED() (++g_launches)
+unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend_launches; }
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ---- constant tables ----------------------------------------------------------------------------------
 __constant__ float c_window[NFFT];
@@ -882,10 +884,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_defer_chain(const float *__re
 void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
                      ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st) {
     if (n <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<bool> attr_set{false};
+    if (!attr_set.load()) {
         cudaFuncSetAttribute(k_defer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
-        attr_set = true;
+        attr_set.store(true);
     }
     cudaMemsetAsync(scratch, 0x7f, (size_t)n * sizeof(ChainScratch), st);     // best = "no attempt has succeeded"
     k_chain_reset<<<(n + 127) / 128, 128, 0, st>>>(scratch, n);

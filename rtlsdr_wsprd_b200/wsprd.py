@@ -270,6 +270,54 @@ class BatchDecoder:
                 float(self.lib.wspr_ctx_last_sync_cells(self.ctx)))
 
 
+class PipelinedDecoder:
+    """`depth` BatchDecoder contexts, each driven by its own host thread, so consecutive batches overlap on the GPU.
+
+    A decode ends with a tail in which only the few captures that own a hopeless candidate are still busy (one Fano
+    time-out is 810 000 strictly sequential cycles); with several batches in flight the GPU works on the next batch's
+    bulk while the previous one drains, and host<->device copies of one batch hide behind the kernels of another.
+    submit(fn) runs fn(decoder) on a free context and returns a concurrent.futures.Future."""
+
+    def __init__(self, depth, max_captures, samples=NSAMP, device=-1):
+        import concurrent.futures as cf
+        import queue
+        self.depth = int(depth)
+        self.decoders = [BatchDecoder(max_captures, samples, device) for _ in range(self.depth)]
+        self._free = queue.Queue()
+        for d in self.decoders:
+            self._free.put(d)
+        self._pool = cf.ThreadPoolExecutor(max_workers=self.depth)
+
+    def submit(self, fn):
+        def run():
+            d = self._free.get()
+            try:
+                return fn(d)
+            finally:
+                self._free.put(d)
+        return self._pool.submit(run)
+
+    def decode_async(self, I, Q, options=None):
+        """Upload host arrays, decode, download: Future of (spots[ncap, 100], n_results[ncap])."""
+        def job(d):
+            d.upload(I, Q)
+            d.decode(options)
+            return d.download()
+        return self.submit(job)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for d in self.decoders:
+            d.close()
+        self.decoders = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 def decode_batch(I, Q, options=None, device=-1):
     """One-shot batch decode of host arrays I, Q: float32[ncap, samples] -> list of RESULT_DTYPE arrays."""
     lib = library()
