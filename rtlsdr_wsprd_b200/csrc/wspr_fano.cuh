@@ -1,14 +1,22 @@
-// Device-side Fano sequential decoder (K=32, r=1/2; wsprd/fano.c:87-238), latency-tuned.
+// Device-side Fano sequential decoder (K=32, r=1/2; wsprd/fano.c:87-238): lane-dense, branch-free.
 //
-// A decode that fails costs maxcycles*nbits = 810 000 strictly sequential tree moves, so what matters on a GPU thread
-// is the dependent latency of ONE move.  The portable version in wspr_codec.cuh keeps the tree in five indexed
-// arrays (every move is a chain of dependent local-memory round trips, ~30 cycles each).  Here
-//   * the node the decoder stands on (encoder state, path metric, the two sorted branch metrics, branch index) and
-//     the path metric of its parent live in registers: a forward move touches no memory on its critical path,
-//   * a node is one 16-byte record, so stepping back is a single vector load,
-//   * the four branch metrics of a tree level are one 8-byte record fetched at the top of the move.
-// The sequence of moves, the cycle count, the final metric and the decoded bytes are identical to fano.c (checked
-// against the oracle on random symbol vectors, including timeouts, in tests/test_gpu_parity.py).
+// A decode that fails costs maxcycles*nbits = 810 000 strictly sequential tree moves, so two things matter on a GPU:
+// the dependent latency of ONE move, and how many issue slots a move costs.  A thread-per-attempt port of fano.c
+// (the portable version in wspr_codec.cuh) is poor at both: the tree lives in five indexed local arrays (every move a
+// chain of dependent memory round trips) and the 32 lanes of a warp sit on different paths of a branchy loop, so the
+// warp serialises them.  Here every lane of a warp decodes its own attempt and all lanes execute the SAME instruction
+// stream: one loop trip performs whichever of {forward move, tighten threshold, step back} the lane needs, chosen by
+// predicates/selects, so 32 attempts advance per issued instruction.
+//   * The node a lane stands on (encoder state, path metric, packed branch metrics, branch index) and its parent's
+//     metric live in registers; a forward move touches no memory on its critical path.
+//   * Per tree level the four possible (better metric, worse metric, bit) triples are precomputed, so arriving at a
+//     node is a 4-way register select.
+//   * A node record is 16 bytes {enc, gam, metrics | branch index, gam of the parent}: one vector store when a node is
+//     left forwards, one vector load per step back.  Records are interleaved by lane in shared memory
+//     ([element][lane]), which makes the 128-bit accesses of a warp bank-conflict free whatever depth each lane is at.
+//   * A walk back over several nodes costs one loop trip per node but only one Fano cycle, as in fano.c.
+// The move sequence, cycle count, final metric and decoded bytes are identical to fano.c (tests/test_gpu_parity.py
+// checks them against the oracle on random symbol vectors, time-outs included).
 #pragma once
 #include "wspr_codec.cuh"
 
@@ -20,131 +28,10 @@ struct FanoResult {
     unsigned char data[12];
 };
 
-__device__ __forceinline__ int fano_pick(uint2 m, unsigned ls) {   // m = four int16 metrics, index ls
-    const unsigned long long v = ((unsigned long long)m.y << 32) | m.x;
-    return (int)(short)(unsigned short)(v >> (16 * ls));
-}
-
-constexpr int FANO_NODE_WORDS = NBITS + 2;   // uint4 records
-constexpr int FANO_BM_WORDS = NBITS + 1;     // uint2 records
-constexpr int FANO_STATE_BYTES = FANO_NODE_WORDS * 16 + FANO_BM_WORDS * 8 + 8;   // multiple of 16
-
-// node / bm: working storage supplied by the caller -- per-thread local arrays when every lane of a warp decodes
-// (the local-memory interleave keeps that cache friendly), shared memory when a single lane per warp decodes (a lone
-// lane would use 1/32 of every local-memory line and fall out of L1).
-template <typename Poll>
-__device__ __forceinline__ void fano_fast(FanoResult &out, const unsigned char *__restrict__ symbols, const short *__restrict__ mettab,
-                                          int delta, unsigned maxcycles, unsigned stop_after, Poll poll, uint4 *node, uint2 *bm) {
-    constexpr int nbits = NBITS;
-    constexpr int last = nbits - 1, tail = nbits - 31;
-    // node[n] = {enc, gam, tm0 | tm1 << 16, sel} of the nodes on the current path below `pos`
-    // bm[n]   = branch metrics of level n: (symbol pair 00, 01), (10, 11)
-#pragma unroll 1
-    for (int n = 0; n < nbits; n++) {
-        const int a0 = mettab[symbols[2 * n]], a1 = mettab[256 + symbols[2 * n]];
-        const int b0 = mettab[symbols[2 * n + 1]], b1 = mettab[256 + symbols[2 * n + 1]];
-        bm[n] = make_uint2(((unsigned)(a0 + b0) & 0xffffu) | ((unsigned)(a0 + b1) << 16),
-                           ((unsigned)(a1 + b0) & 0xffffu) | ((unsigned)(a1 + b1) << 16));
-        node[n] = make_uint4(0, 0, 0, 0);
-    }
-    bm[nbits] = make_uint2(0, 0);
-    node[nbits] = node[nbits + 1] = make_uint4(0, 0, 0, 0);
-
-    int pos = 0, thr = 0, maxnp = 0;
-    unsigned enc = 0;
-    int gam = 0, pgam = 0, tm0, tm1, sel = 0;     // pgam = path metric of the parent node (valid when pos > 0)
-    {
-        const int m0 = fano_pick(bm[0], 0), m1 = fano_pick(bm[0], 3);   // branch_sym(0) == 0
-        if (m0 > m1) { tm0 = m0; tm1 = m1; }
-        else { tm0 = m1; tm1 = m0; enc = 1; }
-    }
-    const unsigned limit = maxcycles * (unsigned)nbits;
-    const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0;
-    unsigned it;
-    bool stopped = false;
-#pragma unroll 1
-    for (it = 1; it <= limit; it++) {
-        if ((it & 1023u) == 0 && ((stop != 0 && it >= stop) || poll(it))) {
-            stopped = true;
-            break;
-        }
-        const uint2 nbm = bm[pos + 1];            // issued early; only the forward move consumes it
-        if (pos > maxnp) maxnp = pos;
-        const int ng = gam + (sel ? tm1 : tm0);
-        if (ng >= thr) {                          // ---- forward
-            if (gam < thr + delta)
-                while (ng >= thr + delta) thr += delta;
-            node[pos] = make_uint4(enc, (unsigned)gam, ((unsigned)tm0 & 0xffffu) | ((unsigned)tm1 << 16), (unsigned)sel);
-            pgam = gam;
-            gam = ng;
-            unsigned e = enc << 1;
-            pos++;
-            if (pos == last + 1) {
-                enc = e;
-                break;
-            }
-            const unsigned ls = branch_sym(e);
-            const int m0 = fano_pick(nbm, ls);
-            if (pos >= tail) {
-                tm0 = m0;
-            } else {
-                const int m1 = fano_pick(nbm, 3u ^ ls);
-                if (m0 > m1) { tm0 = m0; tm1 = m1; }
-                else { tm0 = m1; tm1 = m0; e |= 1u; }
-            }
-            enc = e;
-            sel = 0;
-            continue;
-        }
-        for (;;) {                                // ---- backward
-            if (pos == 0 || pgam < thr) {
-                thr -= delta;
-                if (sel != 0) {
-                    sel = 0;
-                    enc ^= 1u;
-                }
-                break;
-            }
-            pos--;
-            const uint4 nd = node[pos];
-            const int gp = (pos > 0) ? (int)node[pos - 1].y : 0;
-            enc = nd.x;
-            gam = (int)nd.y;
-            tm0 = (int)(short)(nd.z & 0xffffu);
-            tm1 = (int)(short)(nd.z >> 16);
-            sel = (int)nd.w;
-            pgam = gp;
-            if (pos < tail && sel != 1) {
-                sel++;
-                enc ^= 1u;
-                break;
-            }
-        }
-    }
-    node[pos] = make_uint4(enc, (unsigned)gam, 0, 0);
-    out.metric = (unsigned)gam;
-    for (int b = 0; b < 12; b++) out.data[b] = 0;
-    for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)node[7 + 8 * b].x;
-    out.cycles = it + 1;
-    out.maxnp = (unsigned)maxnp;
-    out.rc = stopped ? FANO_STOPPED : ((it >= limit) ? -1 : 0);   // (a decode in the very last cycle counts as a timeout, fano.c:234)
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Single-lane form for the long runners, tree state in shared memory (a lone lane would use 1/32 of every
-// local-memory line and fall out of L1).  Tuned for the dependent latency of one move:
-//   * per tree level the four possible (better metric, worse metric, bit) triples are precomputed, so arriving at a
-//     node is a 4-way register select instead of two metric fetches, a compare and a swap;
-//   * a node record is 16 bytes {enc, gam, packed metrics | branch index, gam of the parent}: one vector store when a
-//     node is left forwards, ONE vector load per step back (the parent's metric needed for the next test rides along);
-//   * shared memory is addressed through a 32-bit window address held in a register (ld/st.shared), and the
-//     threshold loop is kept a loop -- left alone the compiler re-derives the window base and inserts an integer
-//     division inside the hot loop.
-// ---------------------------------------------------------------------------------------------------------
-struct FanoSharedState {               // one per attempt, 16-byte aligned
-    uint4 lvl[NBITS + 1];              // per level, indexed by the 2-bit branch symbol: packed (tm0, tm1, bit)
-    uint4 node[NBITS + 2];
-};
+constexpr int FANO_LVL_RECORDS = NBITS + 1;      // per lane
+constexpr int FANO_NODE_RECORDS = NBITS + 2;
+// shared memory of one warp: [FANO_LVL_RECORDS + FANO_NODE_RECORDS][32 lanes] uint4
+constexpr int FANO_WARP_SMEM_BYTES = (FANO_LVL_RECORDS + FANO_NODE_RECORDS) * 32 * 16;
 
 __device__ __forceinline__ unsigned fano_pack(int tm0, int tm1, unsigned bit) {   // tm0: bits 0..15, tm1: 16..29, bit: 30
     return ((unsigned)tm0 & 0xffffu) | (((unsigned)tm1 & 0x3fffu) << 16) | (bit << 30);
@@ -160,112 +47,148 @@ __device__ __forceinline__ void sts128(unsigned addr, unsigned x, unsigned y, un
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-template <typename Poll>
-__device__ __forceinline__ void fano_shared(FanoResult &out, const unsigned char *__restrict__ symbols,
-                                            const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
-                                            Poll poll, FanoSharedState &st) {
+struct FanoNoStop {                    // hook: stop() polled every 256 trips by active lanes, success() called on a decode
+    __device__ bool stop() const { return false; }
+    __device__ void success() const {}
+};
+
+// Every lane of the warp must call this together.  `want`: this lane has an attempt to decode (symbols valid).
+// warp_smem: shared-memory byte address (cvta'd) of this warp's FANO_WARP_SMEM_BYTES scratch.
+// stop_after: 0 = run to the reference's limit; else give up (FANO_STOPPED) once that many cycles were spent.
+// hook.stop(): evaluated every 256 trips by active lanes, true abandons the attempt (FANO_STOPPED);
+// hook.success(): called by a lane the moment it decodes.
+// A lane that has finished keeps executing the (uniform) loop as a harmless zombie -- its threshold is parked so high
+// that it only ever tightens it in place -- while its result waits in separate registers; the hot loop therefore
+// carries no per-lane "active" predicate.
+template <typename Hook>
+__device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
+                                           const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
+                                           Hook hook, unsigned warp_smem) {
     constexpr int nbits = NBITS;
-    constexpr int last = nbits - 1, tail = nbits - 31;
+    constexpr int tail = nbits - 31;
+    constexpr int PARKED = 0x3fffffff;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned lvl_base = warp_smem + lane * 16u;                                   // record e of this lane: base + e*512
+    unsigned node_base = warp_smem + (unsigned)FANO_LVL_RECORDS * 512u + lane * 16u;
+    asm volatile("" : "+r"(lvl_base), "+r"(node_base));                            // keep both in registers
 #pragma unroll 1
-    for (int n = 0; n <= nbits; n++) {
-        uint4 e = make_uint4(0, 0, 0, 0);
-        if (n < nbits) {
+    for (int n = 0; n <= nbits; n++) {                                             // (lanes without an attempt get zeros)
+        unsigned w[4] = {0, 0, 0, 0};
+        if (want && n < nbits) {
             const int a0 = mettab[symbols[2 * n]], a1 = mettab[256 + symbols[2 * n]];
             const int b0 = mettab[symbols[2 * n + 1]], b1 = mettab[256 + symbols[2 * n + 1]];
             const int m[4] = {a0 + b0, a0 + b1, a1 + b0, a1 + b1};
-            unsigned w[4];
 #pragma unroll
             for (int ls = 0; ls < 4; ls++) {
                 const int m0 = m[ls], m1 = m[3 ^ ls];
                 if (n >= tail) w[ls] = fano_pack(m0, 0, 0);
                 else w[ls] = (m0 > m1) ? fano_pack(m0, m1, 0) : fano_pack(m1, m0, 1);
             }
-            e = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        st.lvl[n] = e;
-        st.node[n] = make_uint4(0, 0, 0, 0);
+        sts128(lvl_base + 512u * (unsigned)n, w[0], w[1], w[2], w[3]);
     }
-    st.node[nbits + 1] = make_uint4(0, 0, 0, 0);
-    unsigned lvl_base = (unsigned)__cvta_generic_to_shared(&st.lvl[0]);
-    unsigned node_base = (unsigned)__cvta_generic_to_shared(&st.node[0]);
-    asm volatile("" : "+r"(lvl_base), "+r"(node_base));   // opaque: keep the window addresses in registers
-
-    int pos = 0, thr = 0, maxnp = 0;
-    unsigned w = st.lvl[0].x;                     // branch_sym(0) == 0
-    unsigned enc = w >> 30;
-    int gam = 0, pgam = 0, sel = 0;
+#pragma unroll 1
+    for (int n = 0; n < FANO_NODE_RECORDS; n++) sts128(node_base + 512u * (unsigned)n, 0u, 0u, 0u, 0u);
     const unsigned limit = maxcycles * (unsigned)nbits;
-    const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0;
-    unsigned it;
-    bool stopped = false;
+    const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0xffffffffu;
+    const bool smallstep = delta > 10;             // a branch metric is at most +10: one threshold step per move suffices
+    const float inv_delta = 1.0f / (float)delta;
+
+    bool act = want, inback = false;
+    int pos = 0, thr = want ? 0 : PARKED, gam = 0, pgam = 0, sel = 0, maxnp = 0;
+    unsigned it = 0;                               // Fano cycles started so far
+    unsigned w = lds128(lvl_base).x;               // root: branch_sym(0) == 0
+    unsigned enc = w >> 30;
+    int r_rc = -1;                                 // result registers, filled when the lane finishes
+    unsigned r_metric = 0, r_cycles = 0, r_maxnp = 0;
 #pragma unroll 1
-    for (it = 1; it <= limit; it++) {
-        if ((it & 1023u) == 0 && ((stop != 0 && it >= stop) || poll(it))) {
-            stopped = true;
-            break;
+    for (unsigned trip = 0;; trip++) {
+        if ((trip & 255u) == 0u) {                 // housekeeping
+            if (act && !inback && (it >= stop || hook.stop())) {
+                act = false;
+                r_rc = FANO_STOPPED;
+                r_metric = (unsigned)gam;
+                r_cycles = it + 1u;
+                r_maxnp = (unsigned)maxnp;
+                thr = PARKED;
+            }
+            if (!__any_sync(0xffffffffu, act)) break;
         }
-        const uint4 nl = lds128(lvl_base + 16u * (unsigned)(pos + 1));   // issued early; only the forward move uses it
-        maxnp = max(maxnp, pos);
+        // speculative fetches: the level we would move down to, the node we would step back to
+        const uint4 nl = lds128(lvl_base + 512u * (unsigned)(pos + 1));
+        const uint4 nd = lds128(node_base + 512u * (unsigned)max(pos - 1, 0));
         const int ng = gam + (sel ? fano_tm1(w) : fano_tm0(w));
-        if (ng >= thr) {                          // ---- forward
-            if (gam < thr + delta) {
-#pragma unroll 1
-                while (ng >= thr + delta) {
-                    thr += delta;
-                    asm volatile("" : "+r"(thr));  // (keeps this a loop: the closed form needs an integer division)
-                }
-            }
-            sts128(node_base + 16u * (unsigned)pos, enc, (unsigned)gam, w | ((unsigned)sel << 31), (unsigned)pgam);
-            pgam = gam;
-            gam = ng;
-            const unsigned e = enc << 1;
-            pos++;
-            if (pos == last + 1) {
-                enc = e;
-                break;
-            }
-            const unsigned pa = __popc(e & POLY_A), pb = __popc(e & POLY_B);
-            const unsigned wlo = (pb & 1u) ? nl.y : nl.x, whi = (pb & 1u) ? nl.w : nl.z;   // ls = 2*(pa&1) + (pb&1)
-            w = (pa & 1u) ? whi : wlo;
-            enc = e | (w >> 30);
-            sel = 0;
-            continue;
+        const bool newc = !inback;                 // this trip opens a new Fano cycle
+        const bool fwd = newc && (ng >= thr);
+        const bool tig = newc && !fwd && (pos == 0 || pgam < thr);
+        const bool bck = !fwd && !tig;
+        if (newc && it >= limit && act) {           // the reference's loop ends here: time-out (rare, once per lane)
+            act = false;
+            r_rc = -1;
+            r_metric = (unsigned)gam;
+            r_cycles = limit + 2u;
+            r_maxnp = (unsigned)maxnp;
         }
-        if (pos == 0 || pgam < thr) {             // ---- tighten the threshold, stay on this node
-            thr -= delta;
-            enc ^= (unsigned)sel;                 // (sel is 0 or 1: undo the branch flip)
-            sel = 0;
-            continue;
+        it += newc ? 1u : 0u;
+        maxnp = newc ? max(maxnp, pos) : maxnp;
+        // ---- forward: raise the threshold on a first visit, push the node, descend along the better branch
+        int thrF = thr;
+        if (smallstep) {
+            thrF = (gam < thr + delta && ng >= thr + delta) ? thr + delta : thr;
+        } else if (gam < thr + delta) {             // while (ng >= thr + delta) thr += delta
+            const int d = ng - thr;
+            int k = __float2int_rz((float)d * inv_delta);
+            k += ((k + 1) * delta <= d) ? 1 : 0;
+            k -= (k * delta > d) ? 1 : 0;
+            thrF = thr + k * delta;
         }
-#pragma unroll 1
-        for (;;) {                                // ---- step back
-            pos--;
-            const uint4 nd = lds128(node_base + 16u * (unsigned)pos);
-            enc = nd.x;
-            gam = (int)nd.y;
-            w = nd.z & 0x7fffffffu;
-            sel = (int)(nd.z >> 31);
-            pgam = (int)nd.w;
-            if (pos < tail && sel != 1) {         // take the other branch of this node
-                sel = 1;
-                enc ^= 1u;
-                break;
+        if (fwd) sts128(node_base + 512u * (unsigned)pos, enc, (unsigned)gam, w | ((unsigned)sel << 31), (unsigned)pgam);
+        const unsigned e = enc << 1;
+        const unsigned pa = __popc(e & POLY_A) & 1u, pb = __popc(e & POLY_B) & 1u;   // branch symbol = 2*pa + pb
+        const unsigned wlo = pb ? nl.y : nl.x, whi = pb ? nl.w : nl.z;
+        const unsigned wF = pa ? whi : wlo;
+        const unsigned encF = e | (wF >> 30);
+        // ---- step back onto the parent
+        const unsigned encB0 = nd.x, wB = nd.z & 0x7fffffffu;
+        const int selB0 = (int)(nd.z >> 31), pgamB = (int)nd.w;
+        const bool b1 = (pos - 1 < tail) && (selB0 == 0);            // take the parent's other branch
+        const bool b2 = !b1 && (pos - 1 == 0 || pgamB < thr);        // cannot go higher: tighten there
+        const unsigned encB = encB0 ^ (unsigned)(b1 ? 1 : (b2 ? selB0 : 0));
+        const int selB = b1 ? 1 : (b2 ? 0 : selB0);
+        // ---- merge
+        const int dthr = (tig || (bck && b2)) ? delta : 0;
+        thr = fwd ? thrF : thr - dthr;
+        pgam = fwd ? gam : (bck ? pgamB : pgam);
+        gam = fwd ? ng : (bck ? (int)nd.y : gam);
+        enc = fwd ? encF : (bck ? encB : (enc ^ (unsigned)sel));
+        w = fwd ? wF : (bck ? wB : w);
+        sel = fwd ? 0 : (bck ? selB : 0);
+        inback = bck && !b1 && !b2;
+        pos += fwd ? 1 : (bck ? -1 : 0);
+        if (pos == nbits) {                        // reached the last node: decoded (rare, once per lane)
+            if (act) {
+                act = false;
+                r_rc = (it >= limit) ? -1 : 0;     // (a decode in the very last cycle counts as a timeout, fano.c:234)
+                r_metric = (unsigned)gam;
+                r_cycles = it + 1u;
+                r_maxnp = (unsigned)maxnp;
+                if (r_rc == 0) hook.success();
             }
-            if (pos == 0 || pgam < thr) {         // cannot go further up: tighten, stay here
-                thr -= delta;
-                enc ^= (unsigned)sel;
-                sel = 0;
-                break;
-            }
+            pos = nbits - 1;                       // park: stay put, tightening an unreachable threshold
+            thr = PARKED;
+            inback = false;
         }
     }
-    sts128(node_base + 16u * (unsigned)pos, enc, (unsigned)gam, 0u, 0u);
-    out.metric = (unsigned)gam;
+    out.rc = r_rc;
+    out.metric = r_metric;
+    out.cycles = r_cycles;
+    out.maxnp = r_maxnp;
+#pragma unroll
     for (int b = 0; b < 12; b++) out.data[b] = 0;
-    for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)st.node[7 + 8 * b].x;
-    out.cycles = it + 1;
-    out.maxnp = (unsigned)maxnp;
-    out.rc = stopped ? FANO_STOPPED : ((it >= limit) ? -1 : 0);
+    if (want && r_rc == 0) {
+#pragma unroll
+        for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)lds128(node_base + 512u * (unsigned)(7 + 8 * b)).x;
+    }
 }
 
 }  // namespace wspr

@@ -685,35 +685,40 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
 }
 
 // =========================================================================================================
-// K5  Fano decoder (fano.c:87-238), metric table in constant memory.
-//   k_fano_round  jitter-0 attempts of a round, one thread per attempt, at most fano_budget cycles: nearly every
-//                 decodable candidate finishes within a few hundred cycles; the rest is re-run by the side stream
-//   k_fano_solo   one attempt per warp (lane 0) -- the latency-optimal shape for the few long runners: a timeout
-//                 is 810 000 strictly sequential cycles, and lanes of one warp on different tree paths would
-//                 serialise each other
+// K5  Fano decoder (fano.c:87-238), metric table in constant memory, lane-dense branch-free form (wspr_fano.cuh).
+//   k_fano_round  jitter-0 attempts of a round, 32 attempts per warp, at most fano_budget cycles each: nearly every
+//                 decodable candidate finishes within a few hundred cycles; the rest is finished on a side stream
+//   k_chain_fano  all 43 attempts of one parked candidate in one CTA (below)
 // =========================================================================================================
-__device__ __noinline__ void run_fano(Attempt &a, int delta, unsigned maxcycles, unsigned stop_after, uint4 *node, uint2 *bm) {
-    FanoResult r;
-    fano_fast(r, a.sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), node, bm);
-    a.ok = (r.rc == 0);
-    a.unfinished = (r.rc == FANO_STOPPED);
-    a.cycles = r.cycles;
-    for (int k = 0; k < 12; k++) a.dec[k] = r.data[k];
-}
+struct ChainStop {                                             // abandon an attempt once a lower-numbered one decoded
+    int *best;
+    int idt;
+    __device__ bool stop() const { return *(const volatile int *)best < idt; }
+    __device__ void success() const { atomicMin(best, idt); }
+};
+static void fano_attrs();
 
 __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, const int *__restrict__ job_list, int njobs,
                                                    int delta, unsigned maxcycles, unsigned budget) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= njobs) return;
-    Attempt &a = att0[job_list[i]];
-    uint4 node[FANO_NODE_WORDS];                              // every lane decodes: per-thread local arrays
-    uint2 bm[FANO_BM_WORDS];
-    if (a.gate) run_fano(a, delta, maxcycles, budget, node, bm);
+    extern __shared__ __align__(16) unsigned char fano_smem[];
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    Attempt *a = (i < njobs) ? &att0[job_list[i]] : nullptr;
+    const bool want = a != nullptr && a->gate;
+    FanoResult r;
+    fano_dense(r, want, want ? a->sym : nullptr, &c_mettab[0][0], delta, maxcycles, budget, FanoNoStop(),
+               (unsigned)__cvta_generic_to_shared(fano_smem));
+    if (want) {
+        a->ok = (r.rc == 0);
+        a->unfinished = (r.rc == FANO_STOPPED);
+        a->cycles = r.cycles;
+        for (int k = 0; k < 12; k++) a->dec[k] = r.data[k];
+    }
 }
 
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_fano_round<<<(njobs + 31) / 32, 32, 0, st>>>(att0, job_list, njobs, p.delta, p.maxcycles, p.fano_budget);
+    fano_attrs();
+    k_fano_round<<<(njobs + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(att0, job_list, njobs, p.delta, p.maxcycles, p.fano_budget);
     LAUNCHED();
 }
 
@@ -755,163 +760,128 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 }
 
 // ---- deferred candidates (side stream) --------------------------------------------------------------------------
-// CHAIN_CTAS small CTAs own one parked candidate and run what is left of its jitter loop (wsprd.c:741-766) with every attempt in
-// flight at once -- attempt 0 is the unfinished jitter-0 Fano run (now with the reference's full cycle budget),
-// attempts 1..42 are the jittered ones, shift + 3*(+-1..21):
-//   (1) the jittered soft-symbol vectors of this CTA's attempts (a few warps per SM keeps every Fano lane at full speed);
-//   (2) lane 0 of one warp per attempt runs the latency-tuned Fano decoder; an attempt is abandoned as soon as a
-//       lower-numbered one has succeeded -- the reference's sequential loop would never have reached it;
-//   (3) the CTA that finishes last picks the winner = lowest successful attempt, exactly what the sequential loop
-//       returns, and hands the capture back to the rounds.  No barrier with other parked candidates anywhere.
+// What is left of a parked candidate's jitter loop (wsprd.c:741-766) runs with every attempt in flight at once --
+// attempt 0 is the unfinished jitter-0 Fano run (now with the reference's full cycle budget), attempts 1..42 are the
+// jittered ones, shift + 3*(+-1..21):
+//   k_jitter_soft  grid (candidate, jitter): the jittered soft-symbol vectors and their gates (mode 2 of
+//                  sync_and_demodulate + the rms test), written to the candidate's scratch record;
+//   k_chain_fano   one 64-thread CTA per candidate, one lane per attempt, lane-dense Fano; an attempt is abandoned as
+//                  soon as a lower-numbered one has succeeded -- the reference's sequential loop would never have
+//                  reached it.  Winner = lowest successful attempt, exactly what the sequential loop returns; the CTA
+//                  then hands the capture back to the rounds.  No barrier with other parked candidates anywhere.
 // stats: [0] settled by the full-budget jitter-0 run, [1] by a jittered attempt, [2] never decoded
-__global__ void k_chain_reset(ChainScratch *scratch, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) scratch[i].done = 0;
-}
-
-constexpr int CHAIN_WARPS = 8;                                  // attempts per CTA; ceil(43/8) = 6 CTAs share a candidate
-constexpr int CHAIN_THREADS = CHAIN_WARPS * 32;
-constexpr int CHAIN_GROUP = 1;                                  // jitter attempts correlated per sweep (162 <= 256)
-constexpr int CHAIN_CTAS = (NJIT + CHAIN_WARPS - 1) / CHAIN_WARPS;
-
-struct JitterPoll {
-    const volatile int *best;
-    int idt;
-    __device__ bool operator()(unsigned) const { return *best < idt; }
-};
-
-struct ChainShared {
-    float4 tab[2 * SPS];
-    float4 P[CHAIN_GROUP * NSYM];
-    FanoSharedState fano[CHAIN_WARPS];
-    unsigned char sym[CHAIN_WARPS][NSYM + 2];
-    int gate[CHAIN_WARPS];
-};
-
-__global__ void __launch_bounds__(CHAIN_THREADS) k_defer_chain(const float *__restrict__ I, const float *__restrict__ Q,
-                                                               Job *__restrict__ jobs, const Attempt *__restrict__ att0,
-                                                               CapState *__restrict__ caps, const int *__restrict__ defer_list,
-                                                               ChainScratch *__restrict__ scratch, int np, int stride,
-                                                               float minrms, int symfac, int delta, unsigned maxcycles,
-                                                               int *__restrict__ stats) {
-    extern __shared__ __align__(16) unsigned char chain_smem[];
-    ChainShared &sh = *reinterpret_cast<ChainShared *>(chain_smem);
-    const int e = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+__global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
+                                                     const Job *__restrict__ jobs, const Attempt *__restrict__ att0,
+                                                     const int *__restrict__ defer_list, ChainScratch *__restrict__ scratch,
+                                                     int np, int stride, float minrms, int symfac) {
+    __shared__ float4 tab[2 * SPS];
+    __shared__ float4 P[NSYM];
+    const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
     const int cap = defer_list[e];
-    Job &job = jobs[cap];
+    const Job &job = jobs[cap];
     ChainScratch &cs = scratch[e];
-    const int a_first = blockIdx.y * CHAIN_WARPS;              // attempts [a_first, a_first + CHAIN_WARPS) ∩ [0, NJIT)
-    const float f0 = job.freq, drift = job.drift;
-    const int shift = job.shift;
-    const bool shared_tab = (drift == 0.0f);
-    const float minsync2 = pass_minsync2(job.ipass);
-    const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
-    if (t < CHAIN_WARPS) sh.gate[t] = 0;
-    if (shared_tab && gridDim.y > 1) build_tables(f0, sh.tab, t);
-    __syncthreads();
-    if (a_first == 0) {                                        // attempt 0: the parked jitter-0 soft symbols
+    if (idt == 0) {                                            // attempt 0: the parked jitter-0 soft symbols
         const Attempt &a = att0[cap];
-        for (int i = t; i < NSYM; i += CHAIN_THREADS) sh.sym[0][i] = a.sym[i];
-        if (t == 0) sh.gate[0] = a.gate && a.unfinished;
+        for (int i = t; i < NSYM; i += 192) cs.sym[0][i] = a.sym[i];
+        if (t == 0) cs.gate[0] = a.gate && a.unfinished;
+        return;
     }
-    if (gridDim.y > 1) {                                       // (quick mode has no jittered attempts: one CTA, attempt 0 only)
-        const int j_first = max(a_first, 1), j_end = min(a_first + CHAIN_WARPS, NJIT);
-        for (int a0i = j_first; a0i < j_end; a0i += CHAIN_GROUP) {
-            const int g = t / NSYM, sym = t - g * NSYM, idt = a0i + g;
-            if (g < CHAIN_GROUP && idt < j_end) {
-                int ii = (idt + 1) / 2;
-                if (idt % 2 == 1) ii = -ii;
-                ii = 3 * ii;
-                const float fp = shared_tab ? f0 : symbol_freq(f0, drift, sym);
-                sh.P[g * NSYM + sym] = correlate_symbol(ip, qp, np, shift + ii + sym * SPS, shared_tab, sh.tab, fp);
-            }
-            __syncthreads();
-            if (t < CHAIN_GROUP && a0i + t < j_end) {
-                float rms;
-                const int al = a0i + t - a_first;
-                const float s2 = soft_symbols(sh.P + t * NSYM, sh.sym[al], &rms, symfac);
-                sh.gate[al] = (s2 > minsync2) && (rms > minrms);
-            }
-            __syncthreads();
-        }
-    }
+    int ii = (idt + 1) / 2;
+    if (idt % 2 == 1) ii = -ii;
+    ii = 3 * ii;
+    const bool shared_tab = (job.drift == 0.0f);
+    if (shared_tab) build_tables(job.freq, tab, t);
     __syncthreads();
-    {
-        const int idt = a_first + warp;
-        const bool run = idt < NJIT && sh.gate[warp];
-        if (lane == 0 && idt < NJIT) {
-            cs.gate[idt] = run;
-            cs.ok[idt] = 0;
-            cs.unfinished[idt] = 0;
-        }
-        if (run && lane == 0) {
-            FanoResult r;
-            JitterPoll poll{&cs.best, idt};
-            fano_shared(r, sh.sym[warp], &c_mettab[0][0], delta, maxcycles, 0, poll, sh.fano[warp]);
-            {
-                cs.ok[idt] = (r.rc == 0);
-                cs.unfinished[idt] = (r.rc == FANO_STOPPED);
-                cs.cycles[idt] = r.cycles;
-                for (int k = 0; k < 12; k++) cs.dec[idt][k] = r.data[k];
-                if (r.rc == 0) atomicMin(&cs.best, idt);
-            }
-        }
+    if (t < NSYM) {
+        const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
+        const float fp = shared_tab ? job.freq : symbol_freq(job.freq, job.drift, t);
+        P[t] = correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp);
     }
     __syncthreads();
     if (t == 0) {
-        __threadfence();
-        const int arrived = atomicAdd(&cs.done, 1);
-        if (arrived == (int)gridDim.y - 1) {                   // the other CTA's results are complete and visible
-            __threadfence();
-            const int nat = (gridDim.y > 1) ? NJIT : 1;
-            const volatile ChainScratch &v = cs;
-            for (int idt = 0; idt < nat; idt++) {
-                if (v.gate[idt] && !v.unfinished[idt]) job.cycles = v.cycles[idt];
-                if (v.gate[idt] && v.ok[idt]) {
-                    job.decoded = 1;
-                    job.idt = idt;
-                    for (int k = 0; k < 12; k++) job.dec[k] = v.dec[idt][k];
-                    break;
-                }
+        float rms;
+        const float s2 = soft_symbols(P, cs.sym[idt], &rms, symfac);
+        cs.gate[idt] = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
+    }
+}
+
+constexpr int CHAIN_SPLIT = 22;                                // attempts 0..21 on warp 0, 22..42 on warp 1
+__global__ void __launch_bounds__(64) k_chain_fano(Job *__restrict__ jobs, const Attempt *__restrict__ att0,
+                                                   CapState *__restrict__ caps, const int *__restrict__ defer_list,
+                                                   ChainScratch *__restrict__ scratch, int nattempts, int delta,
+                                                   unsigned maxcycles, int *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char fano_smem[];
+    __shared__ int s_best;
+    __shared__ int s_ok[NJIT], s_unfinished[NJIT];
+    __shared__ unsigned s_cycles[NJIT];
+    __shared__ unsigned char s_dec[NJIT][12];
+    const int e = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cap = defer_list[e];
+    ChainScratch &cs = scratch[e];
+    const int idt = warp * CHAIN_SPLIT + lane;
+    const bool mine = (lane < CHAIN_SPLIT) && (idt < nattempts);
+    if (t == 0) s_best = NJIT;
+    if (mine) {
+        s_ok[idt] = 0;
+        s_unfinished[idt] = 0;
+        s_cycles[idt] = 0;
+    }
+    __syncthreads();
+    const bool want = mine && cs.gate[idt];
+    FanoResult r;
+    ChainStop stop{&s_best, idt};
+    fano_dense(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
+               (unsigned)__cvta_generic_to_shared(fano_smem) + (unsigned)warp * FANO_WARP_SMEM_BYTES);
+    if (want) {
+        s_ok[idt] = (r.rc == 0);
+        s_unfinished[idt] = (r.rc == FANO_STOPPED);
+        s_cycles[idt] = r.cycles;
+        for (int k = 0; k < 12; k++) s_dec[idt][k] = r.data[k];
+    }
+    __syncthreads();
+    if (t == 0) {
+        Job &job = jobs[cap];
+        for (int y = 0; y < nattempts; y++) {
+            if (cs.gate[y] && !s_unfinished[y]) job.cycles = s_cycles[y];
+            if (cs.gate[y] && s_ok[y]) {
+                job.decoded = 1;
+                job.idt = y;
+                for (int k = 0; k < 12; k++) job.dec[k] = s_dec[y][k];
+                break;
             }
-            atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
-            __threadfence();
-            *(volatile int *)&caps[cap].phase = PH_RESOLVE;
         }
+        atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
+        __threadfence();
+        *(volatile int *)&caps[cap].phase = PH_RESOLVE;
     }
 }
 
 void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
                      ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st) {
     if (n <= 0) return;
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load()) {
-        cudaFuncSetAttribute(k_defer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainShared));
-        attr_set.store(true);
-    }
-    cudaMemsetAsync(scratch, 0x7f, (size_t)n * sizeof(ChainScratch), st);     // best = "no attempt has succeeded"
-    k_chain_reset<<<(n + 127) / 128, 128, 0, st>>>(scratch, n);
+    fano_attrs();
+    const int nattempts = p.quickmode ? 1 : NJIT;
+    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac);
     LAUNCHED();
-    k_defer_chain<<<dim3(n, p.quickmode ? 1 : CHAIN_CTAS), CHAIN_THREADS, sizeof(ChainShared), st>>>(
-        I, Q, jobs, att0, caps, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac, p.delta, p.maxcycles, stats);
+    k_chain_fano<<<n, 64, 2 * FANO_WARP_SMEM_BYTES, st>>>(jobs, att0, caps, defer_list, scratch, nattempts, p.delta, p.maxcycles,
+                                                         stats);
     LAUNCHED();
 }
 
-// stand-alone Fano batches for the C-ABI test hook wspr_fano_batch(): both storage variants of fano_fast
+// stand-alone Fano batches for the C-ABI test hook wspr_fano_batch(): 32 attempts per warp, or (solo) one per warp
 __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restrict__ symbols, int n, int delta,
                                                   unsigned maxcycles, unsigned stop_after, int solo, int *__restrict__ rc,
                                                   unsigned *__restrict__ metric, unsigned *__restrict__ cycles,
                                                   unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
                                                   unsigned long long *__restrict__ clocks) {
-    __shared__ FanoSharedState s_state;
-    uint4 l_node[FANO_NODE_WORDS];
-    uint2 l_bm[FANO_BM_WORDS];
-    const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (i >= n || (solo && threadIdx.x != 0)) return;
+    extern __shared__ __align__(16) unsigned char fano_smem[];
+    const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * 32 + threadIdx.x);
+    const bool want = i < n && (!solo || threadIdx.x == 0);
     FanoResult r;
     const long long t0 = clock64();
-    if (solo) fano_shared(r, symbols + (size_t)i * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), s_state);
-    else fano_fast(r, symbols + (size_t)i * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoPoll(), l_node, l_bm);
+    fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+               (unsigned)__cvta_generic_to_shared(fano_smem));
+    if (!want) return;
     if (clocks) clocks[i] = (unsigned long long)(clock64() - t0);
     rc[i] = r.rc;
     metric[i] = r.metric;
@@ -919,12 +889,21 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
     maxnp[i] = r.maxnp;
     for (int k = 0; k < 12; k++) data[(size_t)i * 12 + k] = r.data[k];
 }
+static void fano_attrs() {                                    // opt in to > 48 KB of dynamic shared memory, once
+    static std::atomic<bool> done{false};
+    if (done.load()) return;
+    cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    done.store(true);
+}
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
                       cudaStream_t st) {
     if (n <= 0) return;
-    k_fano_test<<<solo ? n : (n + 31) / 32, 32, 0, st>>>(symbols, n, delta, maxcycles, stop_after, solo, rc, metric, cycles, maxnp,
-                                                         data, clocks);
+    fano_attrs();
+    k_fano_test<<<solo ? n : (n + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo, rc, metric,
+                                                                          cycles, maxnp, data, clocks);
     LAUNCHED();
 }
 

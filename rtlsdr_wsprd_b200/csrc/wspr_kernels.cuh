@@ -112,13 +112,10 @@ struct CapState {
     unsigned char chan[NSYM + 2];
 };
 
-// results of the 43 attempts of one parked candidate, shared by the two CTAs that work on it
+// soft symbols and gates of the 43 attempts of one parked candidate (attempt 0 = jitter 0)
 struct ChainScratch {
-    int best;           // lowest attempt number that has decoded so far
-    int done;           // CTAs that have finished
-    int gate[NJIT], ok[NJIT], unfinished[NJIT];
-    unsigned cycles[NJIT];
-    unsigned char dec[NJIT][12];
+    int gate[NJIT + 1];
+    unsigned char sym[NJIT][NSYM + 2];
 };
 
 struct Counters {

@@ -6,7 +6,7 @@ import numpy as np
 import rtlsdr_wsprd_b200 as w
 rng = np.random.default_rng(0)
 base = rng.integers(0, 256, size=(4096, 162), dtype=np.uint8)
-for solo in (1, 0):
+for solo in (1, 0):   # 1: one active lane per warp; 0: 32 attempts per warp
     for n in (1, 1, 8, 148, 1024, 4736, 9472):
         v = base[:n]
         t0 = time.perf_counter()
