@@ -71,7 +71,8 @@ struct SideSlot {
     bool busy = false;
     int *list = nullptr;           // [maxcap] deferred capture indices of one round
     int *count = nullptr;          // device counter of the list
-    ChainScratch *scratch = nullptr;   // [maxcap] attempt results of the parked candidates
+    ChainScratch *scratch = nullptr;   // [chain_cap] soft symbols of the attempts of the parked candidates
+    int chain_cap = 0;
 };
 
 struct wspr_ctx {
@@ -181,7 +182,8 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CK(dalloc(&s.list, B));
         CK(dalloc(&s.count, 1));
-        CK(dalloc(&s.scratch, B));
+        s.chain_cap = std::max(8, std::min(maxcap, 1024));
+        CK(dalloc(&s.scratch, (size_t)s.chain_cap));
     }
     HostTables t;
     host_tables(t);
@@ -250,6 +252,7 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
     p.lagstep = o.quickmode ? 16 : 8;                        // wsprd.c:715-717
     p.nlags = 256 / p.lagstep + 1;
     p.fano_budget = 4096;
+    if (const char *e = getenv("WSPR_FANO_BUDGET")) p.fano_budget = (unsigned)std::max(256, atoi(e));   // tuning knob
     return p;
 }
 
@@ -351,7 +354,9 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             nres_max = c->h_cnt->nres;
             if (ndefer > 0) {                                 // finish them off the critical path
                 c->deferred += ndefer;
-                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list, ndefer, side->scratch, c->stats, p, side->st);
+                for (int off = 0; off < ndefer; off += side->chain_cap)   // (more than chain_cap parked at once: in turn)
+                    launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list + off, std::min(side->chain_cap, ndefer - off),
+                                    side->scratch, c->stats, p, side->st);
                 CK(cudaEventRecord(side->done, side->st));
                 side->busy = true;
             }
@@ -531,6 +536,7 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     int *d_rc = nullptr;
     unsigned *d_m = nullptr, *d_c = nullptr, *d_x = nullptr;
     unsigned long long *d_k = nullptr;
+    unsigned char *d_g = nullptr;                          // (solo & 2): tree state in global memory instead of shared
     int ret = WSPR_OK;
     cudaError_t e = cudaMalloc((void **)&d_sym, (size_t)n * NSYM);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_data, (size_t)n * 12);
@@ -538,10 +544,11 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_m, (size_t)n * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_c, (size_t)n * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_x, (size_t)n * sizeof(unsigned));
+    if (e == cudaSuccess && (solo & 2)) e = cudaMalloc((void **)&d_g, (size_t)((solo & 1) ? n : (n + 31) / 32) * fano_warp_scratch_bytes());
     if (e == cudaSuccess && clocks) e = cudaMalloc((void **)&d_k, (size_t)n * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpy(d_sym, symbols, (size_t)n * NSYM, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        launch_fano_test(d_sym, n, delta, maxcycles, stop_after, solo, d_rc, d_m, d_c, d_x, d_data, d_k, 0);
+        launch_fano_test(d_sym, n, delta, maxcycles, stop_after, solo, d_rc, d_m, d_c, d_x, d_data, d_k, d_g, 0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(rc, d_rc, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
@@ -551,7 +558,7 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     if (e == cudaSuccess) e = cudaMemcpy(data, d_data, (size_t)n * 12, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && clocks) e = cudaMemcpy(clocks, d_k, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) ret = fail(WSPR_ERR_CUDA, "wspr_fano_batch", e);
-    cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k);
+    cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k); cudaFree(d_g);
     return ret;
 }
 

@@ -47,29 +47,53 @@ __device__ __forceinline__ void sts128(unsigned addr, unsigned x, unsigned y, un
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+// Where a warp keeps its level tables and node records: shared memory (lowest latency), or global memory read through
+// L1 (ld.global.ca).  The long-running chains of parked candidates use the latter: a CTA that sits on 170 KB of shared
+// memory for 100+ ms starves the bulk kernels sharing its SM, while L1 lines are a soft claim.
+// `row` = bytes between consecutive records of one lane = 16 * (lanes the scratch is laid out for): 512 for a full
+// warp, 256 when only the first 16 lanes decode (the scratch is then half the size).
+struct FanoSmem {
+    unsigned base, row;
+    __device__ __forceinline__ uint4 ld(unsigned off) const { return lds128(base + off); }
+    __device__ __forceinline__ void st(unsigned off, unsigned x, unsigned y, unsigned z, unsigned w) const { sts128(base + off, x, y, z, w); }
+};
+struct FanoGmem {
+    unsigned char *base;
+    unsigned row;
+    __device__ __forceinline__ uint4 ld(unsigned off) const {
+        uint4 v;
+        asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(base + off) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st(unsigned off, unsigned x, unsigned y, unsigned z, unsigned w) const {
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(base + off), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    }
+};
+
 struct FanoNoStop {                    // hook: stop() polled every 256 trips by active lanes, success() called on a decode
     __device__ bool stop() const { return false; }
     __device__ void success() const {}
 };
 
 // Every lane of the warp must call this together.  `want`: this lane has an attempt to decode (symbols valid).
-// warp_smem: shared-memory byte address (cvta'd) of this warp's FANO_WARP_SMEM_BYTES scratch.
+// mem: this warp's FANO_WARP_SMEM_BYTES of scratch, FanoSmem{cvta'd shared address} or FanoGmem{pointer}.
 // stop_after: 0 = run to the reference's limit; else give up (FANO_STOPPED) once that many cycles were spent.
 // hook.stop(): evaluated every 256 trips by active lanes, true abandons the attempt (FANO_STOPPED);
 // hook.success(): called by a lane the moment it decodes.
 // A lane that has finished keeps executing the (uniform) loop as a harmless zombie -- its threshold is parked so high
 // that it only ever tightens it in place -- while its result waits in separate registers; the hot loop therefore
 // carries no per-lane "active" predicate.
-template <typename Hook>
+template <typename Hook, typename Mem>
 __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
                                            const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
-                                           Hook hook, unsigned warp_smem) {
+                                           Hook hook, Mem mem) {
     constexpr int nbits = NBITS;
     constexpr int tail = nbits - 31;
     constexpr int PARKED = 0x3fffffff;
     const unsigned lane = threadIdx.x & 31u;
-    unsigned lvl_base = warp_smem + lane * 16u;                                   // record e of this lane: base + e*512
-    unsigned node_base = warp_smem + (unsigned)FANO_LVL_RECORDS * 512u + lane * 16u;
+    const unsigned row = mem.row;                                                  // record e of this lane: e*row + lane*16
+    unsigned lvl_base = lane * 16u;
+    unsigned node_base = (unsigned)FANO_LVL_RECORDS * row + lane * 16u;
     asm volatile("" : "+r"(lvl_base), "+r"(node_base));                            // keep both in registers
 #pragma unroll 1
     for (int n = 0; n <= nbits; n++) {                                             // (lanes without an attempt get zeros)
@@ -85,10 +109,10 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
                 else w[ls] = (m0 > m1) ? fano_pack(m0, m1, 0) : fano_pack(m1, m0, 1);
             }
         }
-        sts128(lvl_base + 512u * (unsigned)n, w[0], w[1], w[2], w[3]);
+        mem.st(lvl_base + row * (unsigned)n, w[0], w[1], w[2], w[3]);
     }
 #pragma unroll 1
-    for (int n = 0; n < FANO_NODE_RECORDS; n++) sts128(node_base + 512u * (unsigned)n, 0u, 0u, 0u, 0u);
+    for (int n = 0; n < FANO_NODE_RECORDS; n++) mem.st(node_base + row * (unsigned)n, 0u, 0u, 0u, 0u);
     const unsigned limit = maxcycles * (unsigned)nbits;
     const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0xffffffffu;
     const bool smallstep = delta > 10;             // a branch metric is at most +10: one threshold step per move suffices
@@ -97,7 +121,7 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
     bool act = want, inback = false;
     int pos = 0, thr = want ? 0 : PARKED, gam = 0, pgam = 0, sel = 0, maxnp = 0;
     unsigned it = 0;                               // Fano cycles started so far
-    unsigned w = lds128(lvl_base).x;               // root: branch_sym(0) == 0
+    unsigned w = mem.ld(lvl_base).x;               // root: branch_sym(0) == 0
     unsigned enc = w >> 30;
     int r_rc = -1;                                 // result registers, filled when the lane finishes
     unsigned r_metric = 0, r_cycles = 0, r_maxnp = 0;
@@ -115,8 +139,8 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
             if (!__any_sync(0xffffffffu, act)) break;
         }
         // speculative fetches: the level we would move down to, the node we would step back to
-        const uint4 nl = lds128(lvl_base + 512u * (unsigned)(pos + 1));
-        const uint4 nd = lds128(node_base + 512u * (unsigned)max(pos - 1, 0));
+        const uint4 nl = mem.ld(lvl_base + row * (unsigned)(pos + 1));
+        const uint4 nd = mem.ld(node_base + row * (unsigned)max(pos - 1, 0));
         const int ng = gam + (sel ? fano_tm1(w) : fano_tm0(w));
         const bool newc = !inback;                 // this trip opens a new Fano cycle
         const bool fwd = newc && (ng >= thr);
@@ -142,7 +166,7 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
             k -= (k * delta > d) ? 1 : 0;
             thrF = thr + k * delta;
         }
-        if (fwd) sts128(node_base + 512u * (unsigned)pos, enc, (unsigned)gam, w | ((unsigned)sel << 31), (unsigned)pgam);
+        if (fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w | ((unsigned)sel << 31), (unsigned)pgam);
         const unsigned e = enc << 1;
         const unsigned pa = __popc(e & POLY_A) & 1u, pb = __popc(e & POLY_B) & 1u;   // branch symbol = 2*pa + pb
         const unsigned wlo = pb ? nl.y : nl.x, whi = pb ? nl.w : nl.z;
@@ -187,7 +211,7 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
     for (int b = 0; b < 12; b++) out.data[b] = 0;
     if (want && r_rc == 0) {
 #pragma unroll
-        for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)lds128(node_base + 512u * (unsigned)(7 + 8 * b)).x;
+        for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)mem.ld(node_base + row * (unsigned)(7 + 8 * b)).x;
     }
 }
 

@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, c
     const bool want = a != nullptr && a->gate;
     FanoResult r;
     fano_dense(r, want, want ? a->sym : nullptr, &c_mettab[0][0], delta, maxcycles, budget, FanoNoStop(),
-               (unsigned)__cvta_generic_to_shared(fano_smem));
+               FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
     if (want) {
         a->ok = (r.rc == 0);
         a->unfinished = (r.rc == FANO_STOPPED);
@@ -783,7 +783,11 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
     if (idt == 0) {                                            // attempt 0: the parked jitter-0 soft symbols
         const Attempt &a = att0[cap];
         for (int i = t; i < NSYM; i += 192) cs.sym[0][i] = a.sym[i];
-        if (t == 0) cs.gate[0] = a.gate && a.unfinished;
+        if (t == 0) {
+            cs.gate[0] = a.gate && a.unfinished;
+            cs.best = NJIT;                                    // no attempt has decoded yet
+            cs.done = 0;
+        }
         return;
     }
     int ii = (idt + 1) / 2;
@@ -805,54 +809,59 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
     }
 }
 
-constexpr int CHAIN_SPLIT = 22;                                // attempts 0..21 on warp 0, 22..42 on warp 1
-__global__ void __launch_bounds__(64) k_chain_fano(Job *__restrict__ jobs, const Attempt *__restrict__ att0,
-                                                   CapState *__restrict__ caps, const int *__restrict__ defer_list,
-                                                   ChainScratch *__restrict__ scratch, int nattempts, int delta,
-                                                   unsigned maxcycles, int *__restrict__ stats) {
+// One-warp CTAs.  CTA e < n runs attempts 0..31 of candidate e; CTA n + j runs the remaining attempts 32..42 of candidates
+// 2j (lanes 0..10) and 2j+1 (lanes 16..26).  What a parked candidate holds on an SM is therefore 1.5 small pieces of
+// shared memory instead of one 170 KB block that would crowd the bulk kernels out of that SM for the 100+ ms a hopeless
+// candidate takes.  The piece that finishes last picks the winner and hands the capture back.
+__global__ void __launch_bounds__(32) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
+                                                   const int *__restrict__ defer_list, ChainScratch *__restrict__ scratch, int n,
+                                                   int nattempts, int delta, unsigned maxcycles, int *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
-    __shared__ int s_best;
-    __shared__ int s_ok[NJIT], s_unfinished[NJIT];
-    __shared__ unsigned s_cycles[NJIT];
-    __shared__ unsigned char s_dec[NJIT][12];
-    const int e = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int cap = defer_list[e];
-    ChainScratch &cs = scratch[e];
-    const int idt = warp * CHAIN_SPLIT + lane;
-    const bool mine = (lane < CHAIN_SPLIT) && (idt < nattempts);
-    if (t == 0) s_best = NJIT;
-    if (mine) {
-        s_ok[idt] = 0;
-        s_unfinished[idt] = 0;
-        s_cycles[idt] = 0;
+    const int lane = threadIdx.x;
+    int e, idt;
+    if ((int)blockIdx.x < n) {
+        e = blockIdx.x;
+        idt = lane;
+    } else {
+        e = 2 * ((int)blockIdx.x - n) + (lane >> 4);
+        idt = 32 + (lane & 15);
     }
-    __syncthreads();
+    const bool mine = e < n && idt < nattempts;
+    ChainScratch &cs = scratch[mine ? e : 0];
     const bool want = mine && cs.gate[idt];
     FanoResult r;
-    ChainStop stop{&s_best, idt};
+    ChainStop stop{&cs.best, idt};
     fano_dense(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
-               (unsigned)__cvta_generic_to_shared(fano_smem) + (unsigned)warp * FANO_WARP_SMEM_BYTES);
-    if (want) {
-        s_ok[idt] = (r.rc == 0);
-        s_unfinished[idt] = (r.rc == FANO_STOPPED);
-        s_cycles[idt] = r.cycles;
-        for (int k = 0; k < 12; k++) s_dec[idt][k] = r.data[k];
+               FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
+    if (mine) {
+        cs.ok[idt] = want && (r.rc == 0);
+        cs.unfinished[idt] = want && (r.rc == FANO_STOPPED);
+        cs.cycles[idt] = r.cycles;
+        for (int k = 0; k < 12; k++) cs.dec[idt][k] = r.data[k];
     }
-    __syncthreads();
-    if (t == 0) {
-        Job &job = jobs[cap];
-        for (int y = 0; y < nattempts; y++) {
-            if (cs.gate[y] && !s_unfinished[y]) job.cycles = s_cycles[y];
-            if (cs.gate[y] && s_ok[y]) {
-                job.decoded = 1;
-                job.idt = y;
-                for (int k = 0; k < 12; k++) job.dec[k] = s_dec[y][k];
-                break;
-            }
-        }
-        atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
+    __syncwarp();
+    if (e < n && (lane & 15) == 0 && ((int)blockIdx.x >= n || lane == 0)) {   // one arrival per (piece, candidate)
+        const int pieces = nattempts > 32 ? 2 : 1;
         __threadfence();
-        *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+        const int arrived = atomicAdd(&cs.done, 1);
+        if (arrived == pieces - 1) {                           // the other piece's results are complete and visible
+            __threadfence();
+            const int cap = defer_list[e];
+            Job &job = jobs[cap];
+            const volatile ChainScratch &v = cs;
+            for (int y = 0; y < nattempts; y++) {
+                if (v.gate[y] && !v.unfinished[y]) job.cycles = v.cycles[y];
+                if (v.gate[y] && v.ok[y]) {
+                    job.decoded = 1;
+                    job.idt = y;
+                    for (int k = 0; k < 12; k++) job.dec[k] = v.dec[y][k];
+                    break;
+                }
+            }
+            atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
+            __threadfence();
+            *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+        }
     }
 }
 
@@ -863,8 +872,8 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, C
     const int nattempts = p.quickmode ? 1 : NJIT;
     k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac);
     LAUNCHED();
-    k_chain_fano<<<n, 64, 2 * FANO_WARP_SMEM_BYTES, st>>>(jobs, att0, caps, defer_list, scratch, nattempts, p.delta, p.maxcycles,
-                                                         stats);
+    const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
+    k_chain_fano<<<nctas, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, defer_list, scratch, n, nattempts, p.delta, p.maxcycles, stats);
     LAUNCHED();
 }
 
@@ -873,14 +882,18 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
                                                   unsigned maxcycles, unsigned stop_after, int solo, int *__restrict__ rc,
                                                   unsigned *__restrict__ metric, unsigned *__restrict__ cycles,
                                                   unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
-                                                  unsigned long long *__restrict__ clocks) {
+                                                  unsigned long long *__restrict__ clocks, unsigned char *__restrict__ gmem) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
     const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * 32 + threadIdx.x);
     const bool want = i < n && (!solo || threadIdx.x == 0);
     FanoResult r;
     const long long t0 = clock64();
-    fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-               (unsigned)__cvta_generic_to_shared(fano_smem));
+    if (gmem)
+        fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                   FanoGmem{gmem + (size_t)blockIdx.x * FANO_WARP_SMEM_BYTES, 512u});
+    else
+        fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                   FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
     if (!want) return;
     if (clocks) clocks[i] = (unsigned long long)(clock64() - t0);
     rc[i] = r.rc;
@@ -889,21 +902,23 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
     maxnp[i] = r.maxnp;
     for (int k = 0; k < 12; k++) data[(size_t)i * 12 + k] = r.data[k];
 }
+size_t fano_warp_scratch_bytes() { return FANO_WARP_SMEM_BYTES; }
 static void fano_attrs() {                                    // opt in to > 48 KB of dynamic shared memory, once
     static std::atomic<bool> done{false};
     if (done.load()) return;
     cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     done.store(true);
 }
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
-                      cudaStream_t st) {
+                      unsigned char *gmem, cudaStream_t st) {
     if (n <= 0) return;
     fano_attrs();
-    k_fano_test<<<solo ? n : (n + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo, rc, metric,
-                                                                          cycles, maxnp, data, clocks);
+    const int blocks = (solo & 1) ? n : (n + 31) / 32;
+    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 1, rc, metric,
+                                                                   cycles, maxnp, data, clocks, gmem);
     LAUNCHED();
 }
 

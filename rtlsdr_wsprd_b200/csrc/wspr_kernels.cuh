@@ -114,7 +114,11 @@ struct CapState {
 
 // soft symbols and gates of the 43 attempts of one parked candidate (attempt 0 = jitter 0)
 struct ChainScratch {
-    int gate[NJIT + 1];
+    int best;           // lowest attempt number that has decoded so far
+    int done;           // CTAs of the candidate that have finished
+    int gate[NJIT], ok[NJIT], unfinished[NJIT];
+    unsigned cycles[NJIT];
+    unsigned char dec[NJIT][12];
     unsigned char sym[NJIT][NSYM + 2];
 };
 
@@ -166,7 +170,8 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
 
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
-                      cudaStream_t st);
+                      unsigned char *gmem, cudaStream_t st);
+size_t fano_warp_scratch_bytes();
 
 // front end (rtlsdr_wsprd.c:126-244)
 void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, uint2 *vals,
