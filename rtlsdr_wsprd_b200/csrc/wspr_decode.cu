@@ -345,7 +345,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 kev_used += 2;
                 c->kev_jobs.push_back(h.njobs);
             }
-            launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P1, c->att0, p, c->st);
+            launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->P1, c->att0, p, c->st);
             launch_fano_round(c->att0, c->job_list, h.njobs, p, c->st);
             launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, side->list, side->count, c->cnt, p,
                            c->st);

@@ -21,7 +21,7 @@ unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ---- constant tables ----------------------------------------------------------------------------------
-__constant__ float c_window[NFFT];
+__device__ float c_window_g[NFFT];    // (indexed in bit-reversed order by the lanes: global/L1, not the constant bank)
 __constant__ float c_lpf_w[NFILT];
 __constant__ float c_lpf_psum[NFILT];
 __constant__ float c_min_snr;
@@ -30,7 +30,7 @@ __constant__ short c_mettab[2][256] = WSPR_METTAB_INIT;
 __device__ const double g_tw[256][2] = FFT512_TWIDDLE_INIT;
 
 void upload_tables(const HostTables &t) {
-    cudaMemcpyToSymbol(c_window, t.window, sizeof t.window);
+    cudaMemcpyToSymbol(c_window_g, t.window, sizeof t.window);
     cudaMemcpyToSymbol(c_lpf_w, t.lpf_w, sizeof t.lpf_w);
     cudaMemcpyToSymbol(c_lpf_psum, t.lpf_psum, sizeof t.lpf_psum);
     cudaMemcpyToSymbol(c_min_snr, &t.min_snr, sizeof(float));
@@ -49,47 +49,115 @@ __device__ __forceinline__ double twopidt() { return 2.0 * M_PI * 1.0 / 375.0; }
 // Layout: psT[capture][block][bin] (block-major; the reference's ps[bin][block] transposed, which makes the
 // stores and the per-bin block sums of K2 coalesced).
 // =========================================================================================================
-__global__ void __launch_bounds__(256) k_spectrogram(const float *__restrict__ I, const float *__restrict__ Q,
-                                                     float *__restrict__ psT, const int *__restrict__ list, int stride,
-                                                     int blocks) {
-    __shared__ double re[NFFT], im[NFFT];
-    const int b = blockIdx.x, cap = list[blockIdx.y], t = threadIdx.x;
-    const float *ip = I + (size_t)cap * stride + b * HOP;
-    const float *qp = Q + (size_t)cap * stride + b * HOP;
-    for (int n = t; n < NFFT; n += 256) {
-        float w = c_window[n];
-        float xr = ip[n] * w, xi = qp[n] * w;
-        int r = (int)(__brev((unsigned)n) >> 23);
-        re[r] = (double)xr;
-        im[r] = (double)xi;
+// Work split: 64 threads per transform, 8 points per thread in registers, three register passes of three radix-2
+// stages each (exactly the butterflies of the stand-in, in its order per butterfly) with two exchanges through padded
+// shared memory; two overlapping blocks per CTA share one staged input window.
+constexpr int FFT_PER_CTA = 2;
+constexpr int FFT_SPAN = NFFT + (FFT_PER_CTA - 1) * HOP;      // input samples covered by the CTA's blocks
+struct Cplx {
+    double re, im;
+};
+__device__ __forceinline__ void fft_bf(Cplx &u, Cplx &v, const double2 w) {   // u' = u + W v, v' = u - W v
+    const double tr = w.x * v.re - w.y * v.im;
+    const double ti = w.x * v.im + w.y * v.re;
+    v.re = u.re - tr;
+    v.im = u.im - ti;
+    u.re = u.re + tr;
+    u.im = u.im + ti;
+}
+__device__ __forceinline__ void fft_pass(Cplx v[8], const double2 t1, const double2 t2[2], const double2 t3[4]) {
+#pragma unroll
+    for (int p = 0; p < 8; p += 2) fft_bf(v[p], v[p + 1], t1);
+#pragma unroll
+    for (int p = 0; p < 8; p++)
+        if ((p & 2) == 0) fft_bf(v[p], v[p + 2], t2[p & 1]);
+#pragma unroll
+    for (int p = 0; p < 4; p++) fft_bf(v[p], v[p + 4], t3[p]);
+}
+__device__ __forceinline__ int fft_pad(int idx) { return idx + (idx >> 3); }
+
+__global__ void __launch_bounds__(64 * FFT_PER_CTA) k_spectrogram(const float *__restrict__ I, const float *__restrict__ Q,
+                                                                  float *__restrict__ psT, const int *__restrict__ list,
+                                                                  int stride, int blocks) {
+    __shared__ double2 tw[NFFT / 2];
+    __shared__ float2 xin[FFT_SPAN];
+    __shared__ double s_re[FFT_PER_CTA][NFFT + NFFT / 8], s_im[FFT_PER_CTA][NFFT + NFFT / 8];
+    const int cap = list[blockIdx.y], tid = threadIdx.x, f = tid >> 6, t = tid & 63;
+    const int b0 = blockIdx.x * FFT_PER_CTA, b = b0 + f;
+    const float *ip = I + (size_t)cap * stride + b0 * HOP;
+    const float *qp = Q + (size_t)cap * stride + b0 * HOP;
+    const int span = min(FFT_SPAN, NFFT + (blocks - 1 - b0) * HOP);            // (the last CTA may hold a single block)
+    for (int n = tid; n < span; n += 64 * FFT_PER_CTA) xin[n] = make_float2(ip[n], qp[n]);
+    for (int n = tid; n < NFFT / 2; n += 64 * FFT_PER_CTA) tw[n] = make_double2(g_tw[n][0], g_tw[n][1]);
+    __syncthreads();
+    const bool live = b < blocks;
+    Cplx v[8];
+    double *re = s_re[f], *im = s_im[f];
+    if (live) {
+        // pass 1: stages half = 1, 2, 4 on logical indices 8t..8t+7 (bit-reversed input order)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int n = (int)(__brev((unsigned)(8 * t + k)) >> 23);
+            const float w = c_window_g[n];
+            const float2 x = xin[f * HOP + n];
+            v[k].re = (double)(x.x * w);
+            v[k].im = (double)(x.y * w);
+        }
+        const double2 t2[2] = {tw[0], tw[128]}, t3[4] = {tw[0], tw[64], tw[128], tw[192]};
+        fft_pass(v, tw[0], t2, t3);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            re[fft_pad(8 * t + k)] = v[k].re;
+            im[fft_pad(8 * t + k)] = v[k].im;
+        }
     }
     __syncthreads();
+    if (live) {
+        // pass 2: stages half = 8, 16, 32 on indices hi*64 + m*8 + lo
+        const int hi = t >> 3, lo = t & 7;
 #pragma unroll
-    for (int s = 0; s < 9; s++) {
-        const int half = 1 << s;
-        const int j = t & (half - 1);
-        const int a = ((t >> s) << (s + 1)) + j, bb = a + half;
-        const double wr = g_tw[j << (8 - s)][0], wi = g_tw[j << (8 - s)][1];
-        const double vr = re[bb], vi = im[bb], ur = re[a], ui = im[a];
-        const double tr = wr * vr - wi * vi;
-        const double ti = wr * vi + wi * vr;
-        re[bb] = ur - tr;
-        im[bb] = ui - ti;
-        re[a] = ur + tr;
-        im[a] = ui + ti;
-        __syncthreads();
+        for (int m = 0; m < 8; m++) {
+            v[m].re = re[fft_pad(hi * 64 + m * 8 + lo)];
+            v[m].im = im[fft_pad(hi * 64 + m * 8 + lo)];
+        }
+        const double2 t2[2] = {tw[lo * 16], tw[(8 + lo) * 16]};
+        const double2 t3[4] = {tw[lo * 8], tw[(8 + lo) * 8], tw[(16 + lo) * 8], tw[(24 + lo) * 8]};
+        fft_pass(v, tw[lo * 32], t2, t3);
     }
-    float *out = psT + ((size_t)cap * blocks + b) * NFFT;
-    for (int k = t; k < NFFT; k += 256) {
-        float fr = (float)re[k], fi = (float)im[k];
-        out[(k + NFFT / 2) & (NFFT - 1)] = fr * fr + fi * fi;
+    __syncthreads();
+    if (live) {
+        const int hi = t >> 3, lo = t & 7;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            re[fft_pad(hi * 64 + m * 8 + lo)] = v[m].re;
+            im[fft_pad(hi * 64 + m * 8 + lo)] = v[m].im;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        // pass 3: stages half = 64, 128, 256 on indices q*64 + t
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            v[q].re = re[fft_pad(q * 64 + t)];
+            v[q].im = im[fft_pad(q * 64 + t)];
+        }
+        const double2 t2[2] = {tw[t * 2], tw[(64 + t) * 2]};
+        const double2 t3[4] = {tw[t], tw[64 + t], tw[128 + t], tw[192 + t]};
+        fft_pass(v, tw[t * 4], t2, t3);
+        float *out = psT + ((size_t)cap * blocks + b) * NFFT;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const float fr = (float)v[q].re, fi = (float)v[q].im;
+            out[(q * 64 + t + NFFT / 2) & (NFFT - 1)] = fr * fr + fi * fi;
+        }
     }
 }
 
 void launch_spectrogram(const float *I, const float *Q, float *psT, const int *list, int n, const DecodeParams &p,
                         cudaStream_t st) {
     if (n <= 0 || p.blocks <= 0) return;
-    k_spectrogram<<<dim3(p.blocks, n), 256, 0, st>>>(I, Q, psT, list, p.stride, p.blocks);
+    k_spectrogram<<<dim3((p.blocks + FFT_PER_CTA - 1) / FFT_PER_CTA, n), 64 * FFT_PER_CTA, 0, st>>>(I, Q, psT, list, p.stride,
+                                                                                                   p.blocks);
     LAUNCHED();
 }
 
@@ -301,6 +369,7 @@ __global__ void k_plan(CapState *__restrict__ caps, const Cand *__restrict__ can
         j.snr = c.snr;
         j.worth = 0;
         j.fbest = 0;
+        j.lbest = -1;
         j.decoded = 0;
         j.idt = 0;
         j.cycles = 0;
@@ -486,14 +555,16 @@ __global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const i
     __syncthreads();
     if (t == 0) {
         float best = -1e30f, fbest = 0.0f;
-        int bl = 0;
+        int bl = 0, li = -1;
         const int lagmin = job.shift - 128;
         for (int l = 0; l < nlags; l++)
             if (s_ss[l] > best) {
                 best = s_ss[l];
                 bl = lagmin + l * lagstep;
                 fbest = job.freq;
+                li = l;
             }
+        job.lbest = li;
         job.shift = bl;          // the reference returns best_shift = 0 / freq = 0 if no lag ever won
         job.freq = fbest;
         job.sync1 = best;
@@ -562,10 +633,16 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
 // mode 1: five frequencies at the best lag (:722-726)
 __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I, const float *__restrict__ Q,
                                                     const Job *__restrict__ jobs, const int *__restrict__ job_list,
-                                                    float4 *__restrict__ P1, int np, int stride) {
+                                                    const float4 *__restrict__ P0, float4 *__restrict__ P1, int np,
+                                                    int stride) {
     __shared__ float4 tab[2 * SPS];
     const Job &job = jobs[job_list[blockIdx.x]];
     const int fi = blockIdx.y, t = threadIdx.x;
+    if (fi == 2 && job.lbest >= 0) {       // the centre hypothesis repeats the winning cell row of the lag search exactly
+        if (t < NSYM)
+            P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = P0[((size_t)blockIdx.x * MAXLAGS + job.lbest) * NSYM + t];
+        return;
+    }
     const float fstep = 0.1f;
     const float f0 = job.freq + (float)(fi - 2) * fstep;      // :151
     const bool shared_tab = (job.drift == 0.0f);
@@ -675,10 +752,10 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_
     }
 }
 
-void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P1, Attempt *att0,
-                       const DecodeParams &p, cudaStream_t st) {
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, const float4 *P0, float4 *P1,
+                       Attempt *att0, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P1, p.np, p.stride);
+    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, p.np, p.stride);
     LAUNCHED();
     k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
     LAUNCHED();
@@ -1057,7 +1134,8 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
     }
     __syncthreads();
     const float phi = s_phi[j];
-    const float rc = glibc_cosf(phi), rs = glibc_sinf(phi);
+    float rc, rs;
+    glibc_sincosf(phi, &rs, &rc);
     const int ii = i * SPS + j, k = cs.sub_shift + ii;
     float2 c = make_float2(0.0f, 0.0f);
     if (k > 0 && k < np) {               // :375-381

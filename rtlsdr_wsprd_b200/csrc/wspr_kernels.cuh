@@ -75,6 +75,7 @@ struct Job {
     float snr;
     int worth;          // sync1 > minsync1
     int fbest;          // winning mode-1 hypothesis (its sums are the jitter-0 soft symbols)
+    int lbest;          // index of the winning lag of the mode-0 search (-1: none)
     int decoded;        // a Fano attempt succeeded
     int idt;            // winning jitter attempt
     unsigned cycles;
@@ -148,8 +149,8 @@ void launch_coarse(const float *psT, Cand *cands, const CapState *caps, const in
                    cudaStream_t st);
 void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0,
                       const DecodeParams &p, cudaStream_t st);
-void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P1, Attempt *att0,
-                       const DecodeParams &p, cudaStream_t st);
+void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, const float4 *P0, float4 *P1,
+                       Attempt *att0, const DecodeParams &p, cudaStream_t st);
 // jitter-0 Fano attempts of the round (budgeted) and their triage into the resolve list / the deferred list
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st);
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,

@@ -146,6 +146,40 @@ WMATH float glibc_cosf(float y) {
     return y - y;
 }
 
+// both at once: sinf(y) and cosf(y) share the argument reduction (bit-identical to calling the two above)
+WMATH void glibc_sincosf(float y, float *sp, float *cp) {
+    double x = y;
+    int n;
+    if (abstop12(y) < abstop12(0x1.921fb6p-1f)) {
+        if (abstop12(y) < abstop12(0x1p-12f)) {
+            *sp = y;
+            *cp = 1.0f;
+            return;
+        }
+        const double x2 = x * x;
+        *sp = sincos_poly(x, x2, 0, false);
+        *cp = sincos_poly(x, x2, 1, false);
+        return;
+    }
+    if (abstop12(y) < abstop12(120.0f)) {
+        x = reduce_small(x, &n);
+        const double s = sign_of_quadrant(n & 3), xs = x * s, x2 = x * x;
+        *sp = sincos_poly(xs, x2, n, (n & 2) != 0);
+        *cp = sincos_poly(xs, x2, n ^ 1, (n & 2) != 0);
+        return;
+    }
+    if (abstop12(y) < 0x7f8u) {
+        const uint32_t xi = f2u(y);
+        const int sign = (int)(xi >> 31);
+        x = reduce_big(xi, &n);
+        const double s = sign_of_quadrant((n + sign) & 3), xs = x * s, x2 = x * x;
+        *sp = sincos_poly(xs, x2, n, ((n + sign) & 2) != 0);
+        *cp = sincos_poly(xs, x2, n ^ 1, ((n + sign) & 2) != 0);
+        return;
+    }
+    *sp = *cp = y - y;
+}
+
 // natural log, positive normal arguments only (the decode path passes values in [1, 2))
 WMATH float glibc_logf_normal(float x) {
     const double T[16][2] = {{0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
