@@ -23,6 +23,9 @@ import time
 
 import numpy as np
 
+# several contexts x (1 main + 12 side) streams: give them enough hardware queues (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -35,6 +38,9 @@ NSAMP = 45000
 BYTES_PER_CAPTURE = 360000 + 80 * 10 + 4
 SYNC_BYTES_PER_CANDIDATE = (162 * 256 + 256) * 8 + 33 * 162 * 16      # IQ window read + per-(lag,symbol) tone powers written
 SYNC_FLOP_PER_CANDIDATE = 33 * 162 * 256 * 32                         # 4 tones x (4 mul + 4 add) per sample, unfused
+# dram__bytes_read.sum + dram__bytes_write.sum of k_sync_lags per candidate, from the ncu --set full capture summarised in
+# profiles/r1_ncu_full_sync_lags_sub_lpf.txt (1024 candidates per launch: 344.65 MB read + 75.10 MB written)
+SYNC_DRAM_BYTES_PER_CANDIDATE = (344.651e6 + 75.099e6) / 1024
 
 
 # ---- corpus (host, seeded; identical arrays go to the GPU path and to the CPU reference) --------------------------
@@ -247,7 +253,10 @@ def run_ours(args):
     if sync_ms > 0 and candidates > 0:
         gbs = candidates * SYNC_BYTES_PER_CANDIDATE / (sync_ms * 1e-3) / 1e9
         roofline = {"kernel": "k_sync_lags (sync_and_demodulate mode 0)", "bound": "hbm", "achieved": round(gbs, 2), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(gbs / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": round(gbs / hbm_peak, 5),
+                    "traffic": int(candidates / max(sync_launches, 1) * SYNC_DRAM_BYTES_PER_CANDIDATE),
+                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_sync_lags_sub_lpf.txt, scaled to the mean candidates per launch",
+                    "peak_source": peak_src,
                     "launches": sync_launches, "avg_launch_ms": round(sync_ms / max(sync_launches, 1), 4),
                     "note": "FP32-issue bound, not HBM bound: %.2f TFLOP/s unfused fp32 (%.3g flop per candidate)"
                             % (candidates * SYNC_FLOP_PER_CANDIDATE / (sync_ms * 1e-3) / 1e12, SYNC_FLOP_PER_CANDIDATE)}
@@ -340,13 +349,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--captures", type=int, default=CAPTURES_PER_GPU, help="captures per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=96, help="captures decoded by the CPU baseline / parity leg")
     ap.add_argument("--no-frontend", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight per GPU (contexts driven by host threads)")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight per GPU (contexts driven by host threads)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -1,0 +1,9 @@
+"""Print the headline fields of bench.py JSON lines read from stdin (one per line); extra args are echoed as a label."""
+import json, sys
+for line in sys.stdin:
+    line = line.strip()
+    if not line.startswith("{"):
+        continue
+    d = json.loads(line)
+    print(" ".join(sys.argv[1:]), "depth", d.get("config", {}).get("batches_in_flight"), "value", d.get("value"), "e2e", d.get("e2e", {}).get("value"),
+          "ms/step", d.get("ms_per_step"), "sched", d.get("schedule"), flush=True)
