@@ -265,7 +265,7 @@ def run_ours(args):
     # ---- front end kernel (the HBM-bound one), short live measurement on rank 0 ----
     frontend = None
     if rank == 0 and not args.no_frontend:
-        nstreams, n_iq = 4, 288_000_000
+        nstreams, n_iq = 8, 288_000_000
         stride = 2 * n_iq + 16
         raw = torch.randint(0, 256, (nstreams * stride,), dtype=torch.uint8, device="cuda")
         fI = torch.zeros((nstreams, NSAMP), dtype=torch.float32, device="cuda")

@@ -175,8 +175,8 @@ void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned m
 size_t fano_warp_scratch_bytes();
 
 // front end (rtlsdr_wsprd.c:126-244)
-void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, uint2 *vals,
-                     float *I, float *Q, int out_stride, int max_out, cudaStream_t st);
+void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, float *I,
+                     float *Q, int out_stride, int max_out, cudaStream_t st);
 int decimate_outputs(size_t n_iq);
 
 unsigned long long kernel_launch_count();
