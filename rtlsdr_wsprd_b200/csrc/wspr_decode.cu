@@ -80,6 +80,7 @@ struct wspr_ctx {
     int ncap = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_wait = nullptr;   // blocking-sync event: host threads sleep instead of spinning while the GPU works
     float *I = nullptr, *Q = nullptr, *psT = nullptr, *smspec = nullptr;
     Cand *cands = nullptr;
     CapState *caps = nullptr;
@@ -126,6 +127,7 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -145,6 +147,7 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
     size_t B = (size_t)maxcap;
     CK(dalloc(&c->I, B * c->stride));
     CK(dalloc(&c->Q, B * c->stride));
@@ -179,7 +182,7 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     }
     for (SideSlot &s : c->side) {
         CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming));
         CK(dalloc(&s.list, B));
         CK(dalloc(&s.count, 1));
         s.chain_cap = std::max(8, std::min(maxcap, 1024));
@@ -256,10 +259,17 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
     return p;
 }
 
+// wait for everything issued on the context's stream so far, yielding the CPU (several contexts per GPU and several
+// GPUs per host are each driven by a host thread; spinning in cudaStreamSynchronize would oversubscribe the cores)
+static int wait_stream(wspr_ctx *c) {
+    CK(cudaEventRecord(c->ev_wait, c->st));
+    CK(cudaEventSynchronize(c->ev_wait));
+    return WSPR_OK;
+}
+
 static int read_counters(wspr_ctx *c) {
     CK(cudaMemcpyAsync(c->h_cnt, c->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    return WSPR_OK;
+    return wait_stream(c);
 }
 
 // a side slot whose previous work has completed (waits for the oldest one if all are in flight)
@@ -370,7 +380,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     launch_finish(c->caps, c->spots, c->nres, ncap, c->st);
     CK(cudaMemcpyAsync(c->h_stats, c->stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(c->ev1, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    if (wait_stream(c)) return WSPR_ERR_CUDA;
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     for (size_t k = 0; k + 1 < kev_used; k += 2) {
         float ms = 0;
@@ -411,8 +421,7 @@ extern "C" int wspr_ctx_download(wspr_ctx *c, decoder_results *out, int *n_resul
     size_t w = (size_t)c->np * sizeof(float);
     if (I_out) CK(cudaMemcpy2DAsync(I_out, w, c->I, (size_t)c->stride * sizeof(float), w, ncap, cudaMemcpyDeviceToHost, c->st));
     if (Q_out) CK(cudaMemcpy2DAsync(Q_out, w, c->Q, (size_t)c->stride * sizeof(float), w, ncap, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    return WSPR_OK;
+    return wait_stream(c);
 }
 
 // ---- stage-level access ----

@@ -376,6 +376,34 @@ def spot_line(r):
                                                    r["call"].decode(), r["loc"].decode(), r["pwr"].decode())
 
 
+def print_spots_lines(results, when=None):
+    """printSpots (rtlsdr_wsprd.c:447-474): the daemon's per-slot report.  `when`: time.struct_time (UTC) of the slot."""
+    import time as _time
+    g = when or _time.gmtime()
+    stamp = "%04d-%02d-%02d %02d:%02dz" % (g.tm_year, g.tm_mon, g.tm_mday, g.tm_hour, g.tm_min)
+    if len(results) == 0:
+        return ["No spot " + stamp]
+    return ["Spot :  %s %6.2f %6.2f %10.6f %2d %7s %6s %2s" % (stamp, r["snr"], r["dt"], r["freq"], int(r["drift"]),
+                                                             r["call"].decode(), r["loc"].decode(), r["pwr"].decode())
+            for r in results]
+
+
+def wsprnet_urls(results, rcall, rloc, dialfreq, when=None, version="rtlsdr-056"):
+    """The report URLs postSpots would request (rtlsdr_wsprd.c:366-444); nothing is sent from here.  rcall/rloc are
+    percent-escaped like curl_easy_escape does; `version` = the reference's wsprnet_app_version (rtlsdr_wsprd.c:122)."""
+    import time as _time
+    from urllib.parse import quote
+    g = when or _time.gmtime()
+    rc, rl = quote(rcall, safe="-._~"), quote(rloc, safe="-._~")
+    if len(results) == 0:
+        return ["https://wsprnet.org/post?function=wsprstat&rcall=%s&rgrid=%s&rqrg=%.6f&tpct=%.2f&tqrg=%.6f&dbm=%d&version=%s&mode=2"
+                % (rc, rl, dialfreq / 1e6, 0.0, dialfreq / 1e6, 0, version)]
+    return ["https://wsprnet.org/post?function=wspr&rcall=%s&rgrid=%s&rqrg=%.6f&date=%02d%02d%02d&time=%02d%02d&sig=%.0f&dt=%.1f"
+            "&tqrg=%.6f&tcall=%s&tgrid=%s&dbm=%s&version=%s&mode=2"
+            % (rc, rl, r["freq"], g.tm_year % 100, g.tm_mon, g.tm_mday, g.tm_hour, g.tm_min, r["snr"], r["dt"], r["freq"],
+               r["call"].decode(), r["loc"].decode(), r["pwr"].decode(), version) for r in results]
+
+
 def normalise_half(i, q):
     """Peak normalisation to 0.5 (rtlsdr_wsprd.c:291-305, :575-589): scale = (float)(0.5 / max), float multiply."""
     m = np.float32(1e-24)

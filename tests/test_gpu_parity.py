@@ -257,6 +257,34 @@ def test_subtract_signal2_abi_against_reference_golden():
         assert np.array_equal(ia, st["sub_%d_i" % dft]) and np.array_equal(qa, st["sub_%d_q" % dft])
 
 
+def test_pipelined_contexts_do_not_interfere():
+    """Three batches in flight on three contexts driven by three host threads (what bench.py does): every batch still
+    decodes exactly like the oracle."""
+    batches = [H.make_corpus(3, 6, start=1200 + 10 * k)[:2] for k in range(3)] + [H.make_corpus(2, 12, start=1300)[:2]]
+    with w.PipelinedDecoder(3, 12) as pipe:
+        futs = [pipe.decode_async(I, Q) for I, Q in batches for _ in range(2)]
+        outs = [f.result() for f in futs]
+    for k, (I, Q) in enumerate(batches):
+        for rep in range(2):
+            spots, n = outs[2 * k + rep]
+            for c in range(len(I)):
+                a, _, _ = po.decode(po.oracle(), I[c], Q[c])
+                assert H.results_equal(a, spots[c, : n[c]]), (k, rep, c, H.diff_results(a, spots[c, : n[c]]))
+
+
+@pytest.mark.parametrize("opt", [dict(quickmode=1), dict(subtraction=0), dict(npasses=1), dict(npasses=3)])
+def test_option_variants_on_weak_signals(opt):
+    """Options against the oracle on captures that park candidates (long Fano runs, jitter search): quick mode has no
+    jitter loop, subtraction off makes pass 0 order-free, a third pass changes drift range and minsync2 (wsprd.c:524-531)."""
+    n = 3
+    I = np.zeros((n, corpus.NSAMP), np.float32)
+    Q = np.zeros_like(I)
+    for c in range(n):
+        plan = corpus.ten_signal_plan(950 + c, snrs=np.arange(-30.0, -19.0, 2.0))
+        I[c], Q[c] = corpus.make_capture(9, 950 + c, plan, H.channel_symbols)
+    assert_batch_equals_oracle(I, Q, w.default_options(**opt))
+
+
 def test_fano_kernel_against_oracle_random_vectors():
     """K5 alone: random soft-symbol vectors from clean to hopeless, both storage variants of the device decoder, against
     fano() of the oracle (return code, metric, cycle count, deepest node, decoded bytes); timeouts at a reduced maxcycles
