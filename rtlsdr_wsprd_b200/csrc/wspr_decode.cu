@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sched.h>
 #include <string.h>
 
 #include <algorithm>
@@ -261,10 +262,25 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
 
 // wait for everything issued on the context's stream so far, yielding the CPU (several contexts per GPU and several
 // GPUs per host are each driven by a host thread; spinning in cudaStreamSynchronize would oversubscribe the cores)
+static bool wait_blocks() {                                    // WSPR_WAIT=block: sleep in the driver instead of polling
+    static const bool b = [] { const char *e = getenv("WSPR_WAIT"); return e && e[0] == 'b'; }();
+    return b;
+}
+static int wait_event(cudaEvent_t ev) {
+    if (!wait_blocks()) {                                      // poll, giving the core away whenever someone else wants it
+        for (;;) {
+            cudaError_t q = cudaEventQuery(ev);
+            if (q == cudaSuccess) return WSPR_OK;
+            if (q != cudaErrorNotReady) return fail(WSPR_ERR_CUDA, "cudaEventQuery", q);
+            sched_yield();
+        }
+    }
+    CK(cudaEventSynchronize(ev));
+    return WSPR_OK;
+}
 static int wait_stream(wspr_ctx *c) {
     CK(cudaEventRecord(c->ev_wait, c->st));
-    CK(cudaEventSynchronize(c->ev_wait));
-    return WSPR_OK;
+    return wait_event(c->ev_wait);
 }
 
 static int read_counters(wspr_ctx *c) {
@@ -282,7 +298,7 @@ static int acquire_side(wspr_ctx *c, SideSlot **out) {
                 return WSPR_OK;
             }
         }
-        CK(cudaEventSynchronize(c->side[0].done));
+        if (wait_event(c->side[0].done)) return WSPR_ERR_CUDA;
     }
     return fail(WSPR_ERR_CUDA, "no side stream available");
 }
@@ -290,7 +306,7 @@ static int acquire_side(wspr_ctx *c, SideSlot **out) {
 static int wait_any_side(wspr_ctx *c) {
     for (SideSlot &s : c->side)
         if (s.busy) {
-            CK(cudaEventSynchronize(s.done));
+            if (wait_event(s.done)) return WSPR_ERR_CUDA;
             s.busy = false;
             return WSPR_OK;
         }

@@ -7,6 +7,7 @@
 #include <math_constants.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "fft512_twiddle.h"
 #include "wspr_fano.cuh"
@@ -950,7 +951,10 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, C
     k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac);
     LAUNCHED();
     const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
-    k_chain_fano<<<nctas, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, defer_list, scratch, n, nattempts, p.delta, p.maxcycles, stats);
+    // WSPR_DEBUG_CHAIN_MAXCYCLES: experiment knob (wrong results!) to measure what the long Fano runs cost
+    static const unsigned dbg_maxcycles = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
+    k_chain_fano<<<nctas, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, defer_list, scratch, n, nattempts, p.delta,
+                                                         dbg_maxcycles ? dbg_maxcycles : p.maxcycles, stats);
     LAUNCHED();
 }
 

@@ -52,11 +52,11 @@ def gpu_decode(I, Q, options=None, samples=True):
         return d.download(samples=samples)
 
 
-def assert_batch_equals_oracle(I, Q, options=None):
-    spots, n, Io, Qo = gpu_decode(I, Q, options)
+def assert_batch_equals_oracle(I, Q, **opt):
+    spots, n, Io, Qo = gpu_decode(I, Q, w.default_options(**opt))
     total = 0
     for c in range(len(I)):
-        a, ia, qa = po.decode(po.oracle(), I[c], Q[c], options)
+        a, ia, qa = po.decode(po.oracle(), I[c], Q[c], po.default_options(**opt))
         b = spots[c, : n[c]]
         assert H.results_equal(a, b), (c, H.diff_results(a, b))
         assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c]), c
@@ -282,7 +282,7 @@ def test_option_variants_on_weak_signals(opt):
     for c in range(n):
         plan = corpus.ten_signal_plan(950 + c, snrs=np.arange(-30.0, -19.0, 2.0))
         I[c], Q[c] = corpus.make_capture(9, 950 + c, plan, H.channel_symbols)
-    assert_batch_equals_oracle(I, Q, w.default_options(**opt))
+    assert_batch_equals_oracle(I, Q, **opt)
 
 
 def test_fano_kernel_against_oracle_random_vectors():
