@@ -30,7 +30,7 @@ struct decoder_options {
     char rcall[13];
     char rloc[7];
     int quickmode;
-    int usehashtable;  /* persistent hashtable.txt (reference -H): not supported yet, ignored */
+    int usehashtable;  /* persistent hashtable.txt in the CWD (reference -H, wsprd.c:481-494,842-852) */
     int npasses;
     int subtraction;
 };

@@ -347,30 +347,35 @@ struct DenseHashStore {
 struct HashEntry {
     int h;
     char call[CALL_LEN];
-    char pad[3];
+    char loc[LOC_LEN];             // locator stored with the call by type-1 messages ("" = none); only read by the -H write-back
+    char pad[2];
 };
 struct ListHashStore {
     HashEntry *e;
     int *count;
     int cap;
+    const char *preload;           // [32768][13] calls read from hashtable.txt (reference -H, wsprd.c:481-494), or null
     WHD const char *get(int h) const {
         for (int i = *count - 1; i >= 0; i--)
             if (e[i].h == h) return e[i].call;
-        return "";
+        return preload ? preload + (size_t)h * CALL_LEN : "";
+    }
+    WHD HashEntry *slot(int h) {
+        for (int i = 0; i < *count; i++)
+            if (e[i].h == h) return &e[i];
+        if (*count >= cap) return nullptr;
+        HashEntry *n = &e[(*count)++];
+        n->h = h;
+        n->call[0] = 0;
+        n->loc[0] = 0;
+        return n;
     }
     WHD void put_call(int h, const char *s) {
-        for (int i = 0; i < *count; i++)
-            if (e[i].h == h) {
-                s_copy(e[i].call, CALL_LEN, s);
-                return;
-            }
-        if (*count < cap) {
-            e[*count].h = h;
-            s_copy(e[*count].call, CALL_LEN, s);
-            (*count)++;
-        }
+        if (HashEntry *n = slot(h)) s_copy(n->call, CALL_LEN, s);
     }
-    WHD void put_loc(int, const char *) {}   // the locator table is write-only on the decode path
+    WHD void put_loc(int h, const char *s) {   // (always follows put_call of the same hash, wsprd_utils.c:258-259)
+        if (HashEntry *n = slot(h)) s_copy(n->loc, LOC_LEN, s);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -95,6 +95,7 @@ struct wspr_ctx {
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
     Counters *h_cnt = nullptr;     // pinned host mirror
+    char *preload = nullptr;       // device [32768][13]: hashtable.txt calls (allocated on the first -H decode)
     int *stats = nullptr;          // device [8]: how deferred candidates were settled
     int h_stats[8] = {0};
     SideSlot side[NSIDE];
@@ -114,7 +115,7 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
-                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt, c->stats};
+                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt, c->stats, c->preload};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (SideSlot &s : c->side) {
@@ -255,6 +256,7 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
     p.maxcycles = 10000;
     p.lagstep = o.quickmode ? 16 : 8;                        // wsprd.c:715-717
     p.nlags = 256 / p.lagstep + 1;
+    p.preload = nullptr;
     p.fano_budget = 4096;
     if (const char *e = getenv("WSPR_FANO_BUDGET")) p.fano_budget = (unsigned)std::max(256, atoi(e));   // tuning knob
     return p;
@@ -313,11 +315,73 @@ static int wait_any_side(wspr_ctx *c) {
     return fail(WSPR_ERR_CUDA, "scheduler stalled: captures parked but no side stream is in flight");
 }
 
+// ---- options.usehashtable (reference -H): hashtable.txt in the CWD, wsprd.c:481-494 and :842-852 ----
+constexpr int HT_SIZE = 32768;                                // HASHTAB_SIZE, wsprd/wsprd.h
+struct HostHashTables {
+    std::vector<char> calls, locs;                            // [32768][13], [32768][5]
+    HostHashTables() : calls((size_t)HT_SIZE * CALL_LEN, 0), locs((size_t)HT_SIZE * LOC_LEN, 0) {}
+};
+static void hashtable_read(HostHashTables &t) {
+    FILE *f = fopen("hashtable.txt", "r+");
+    if (!f) return;
+    char line[80], hcall[80] = "", hgrid[80];
+    int nh = -1;                                              // (like the reference, a line that does not parse repeats the previous entry)
+    while (fgets(line, sizeof line, f) != NULL) {
+        hgrid[0] = 0;
+        sscanf(line, "%d %s %s", &nh, hcall, hgrid);
+        if (nh >= 0 && nh < HT_SIZE) {
+            snprintf(t.calls.data() + (size_t)nh * CALL_LEN, CALL_LEN, "%s", hcall);
+            if (strlen(hgrid) > 0) snprintf(t.locs.data() + (size_t)nh * LOC_LEN, LOC_LEN, "%s", hgrid);
+        }
+    }
+    fclose(f);
+}
+static void hashtable_write(const HostHashTables &t) {
+    FILE *f = fopen("hashtable.txt", "w");
+    if (!f) return;
+    for (int i = 0; i < HT_SIZE; i++)
+        if (t.calls[(size_t)i * CALL_LEN] != 0)
+            fprintf(f, "%5d %s %s\n", i, t.calls.data() + (size_t)i * CALL_LEN, t.locs.data() + (size_t)i * LOC_LEN);
+    fclose(f);
+}
+// entries the captures added during the decode, merged in capture order (one capture = the reference's semantics; with
+// several captures in a batch every capture saw the table as it was on entry, and later captures win on write-back)
+static int hashtable_merge(wspr_ctx *c, HostHashTables &t) {
+    std::vector<CapState> caps(c->ncap);
+    CK(cudaMemcpyAsync(caps.data(), c->caps, (size_t)c->ncap * sizeof(CapState), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (const CapState &cs : caps)
+        for (int i = 0; i < cs.nhash && i < HASH_CAP; i++) {
+            const HashEntry &e = cs.hash[i];
+            if (e.h < 0 || e.h >= HT_SIZE) continue;
+            snprintf(t.calls.data() + (size_t)e.h * CALL_LEN, CALL_LEN, "%s", e.call);
+            if (e.loc[0]) snprintf(t.locs.data() + (size_t)e.h * LOC_LEN, LOC_LEN, "%s", e.loc);
+        }
+    return WSPR_OK;
+}
+
 extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     if (!c) return fail(WSPR_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     const int ncap = c->ncap;
-    const DecodeParams p = make_params(c, o);
+    DecodeParams p = make_params(c, o);
+    HostHashTables *ht = nullptr;
+    if (o.usehashtable && ncap > 0) {
+        ht = new HostHashTables();
+        hashtable_read(*ht);
+        cudaError_t e = c->preload ? cudaSuccess : cudaMalloc((void **)&c->preload, ht->calls.size());
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->preload, ht->calls.data(), ht->calls.size(), cudaMemcpyHostToDevice, c->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        if (e != cudaSuccess) {
+            delete ht;
+            return fail(WSPR_ERR_CUDA, "hashtable upload", e);
+        }
+        p.preload = c->preload;
+    }
+    struct HtGuard {
+        HostHashTables *h;
+        ~HtGuard() { delete h; }
+    } ht_guard{ht};
     c->sync_ms = 0.0f;
     c->sync_launches = 0;
     c->sync_cells = 0.0;
@@ -398,6 +462,10 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     CK(cudaEventRecord(c->ev1, c->st));
     if (wait_stream(c)) return WSPR_ERR_CUDA;
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (ht) {
+        if (hashtable_merge(c, *ht)) return WSPR_ERR_CUDA;
+        hashtable_write(*ht);
+    }
     for (size_t k = 0; k + 1 < kev_used; k += 2) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->kev[k], c->kev[k + 1]));

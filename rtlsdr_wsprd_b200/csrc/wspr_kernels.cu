@@ -43,6 +43,34 @@ __device__ __forceinline__ double twopidt() { return 2.0 * M_PI * 1.0 / 375.0; }
 #define W_DF (375.0 / 256.0)
 #define W_HALF_DF (375.0 / 256.0 / 2.0)
 
+// ---- packed binary32 pairs (FFMA2) ----------------------------------------------------------------------
+// The correlation and low-pass kernels are bound by the FP32 pipe AND by issue slots; sm_100 can carry two
+// independent binary32 operations in one instruction (fma.rn.f32x2).  The reference rounds every product and every
+// sum separately, so the packed forms below are an exact product (a*b + -0.0: the addend changes neither the value
+// nor the sign of any product, zeros included) and an exact sum (a*1.0 + b).  ptxas folds fma(fma(a,b,-0),1,c) into
+// fma(a,b,c) when it can see the two constants -- it even contracts mul.rn.f32x2 + add.rn.f32x2 under -fmad=false --
+// so they are handed to the kernels as run-time arguments (PK_NEGZERO, PK_ONE), which it cannot fold.
+// tests/test_abi_cpu.py counts the FFMA2 instructions of the built kernels to catch a toolchain that fuses anyway.
+typedef unsigned long long pk2;                                  // low word = first float
+constexpr pk2 PK_NEGZERO = 0x8000000080000000ull, PK_ONE = 0x3f8000003f800000ull;
+__device__ __forceinline__ pk2 pk_make(float lo, float hi) {
+    pk2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float pk_lo(pk2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float pk_hi(pk2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b, pk2 negzero) {
+    pk2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(negzero));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b, pk2 one) {
+    pk2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(one), "l"(b));
+    return d;
+}
+
 // =========================================================================================================
 // K1  spectrogram: 512-point windowed FFT every 128 samples, |X|^2, fftshift (wsprd.c:536-553).
 // The transform is the binary64 radix-2 DIT graph of the oracle's FFTW stand-in (FFTW itself is an
@@ -417,26 +445,6 @@ __device__ __forceinline__ void tone_seeds(float fp, float cd[4], float sd[4]) {
     cd[2] = glibc_cosf(d2); sd[2] = glibc_sinf(d2);
     cd[3] = glibc_cosf(d3); sd[3] = glibc_sinf(d3);
 }
-// shared phasor tables, layout tab[j] = {c0,s0,c1,s1}, tab[256+j] = {c2,s2,c3,s3}; threads 0..3 run the
-// recurrences (:174-188).  Caller synchronises.
-__device__ __forceinline__ void build_tables(float fp, float4 *tab, int t) {
-    if (t < 4) {
-        float cd[4], sd[4];
-        tone_seeds(fp, cd, sd);
-        const float cdt = cd[t], sdt = sd[t];
-        float *base = reinterpret_cast<float *>(tab) + (t >> 1) * (SPS * 4) + (t & 1) * 2;
-        float c = 1.0f, s = 0.0f;
-        for (int j = 0; j < SPS; j++) {
-            base[j * 4] = c;
-            base[j * 4 + 1] = s;
-            float cn = c * cdt - s * sdt;
-            float sn = c * sdt + s * cdt;
-            c = cn;
-            s = sn;
-        }
-    }
-}
-
 struct Acc8 {
     float ai[4], aq[4];
 };
@@ -458,20 +466,44 @@ __device__ __forceinline__ float4 acc_power(const Acc8 &a) {   // :211-214  (dou
 
 // ---- mode 0: all lags of a group of SYMS_PER_CTA symbols, IQ window staged in shared memory ----------------
 // The window is stored transposed, sample m at [m % 8][m / 8], so that lanes holding consecutive lags (8 samples
-// apart) read consecutive shared-memory words.
-constexpr int SYMS_PER_CTA = 6;
-constexpr int LAG_WIN = SYMS_PER_CTA * SPS + SPS;          // 1792 samples cover every lag of the group
-constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 225
-constexpr int LAG_THREADS = 32 * (SYMS_PER_CTA + 1);       // 224
+// apart) read consecutive shared-memory words.  The cells of the group are numbered lag-fastest and dealt to the
+// threads in that order (cell q = lag + nlags*symbol): 33 x 18 = 594 cells fill 18.6 of the CTA's 19 warps, and the
+// window word a lane reads is q - symbol, i.e. consecutive across a warp.
+// Shared phasor tables for the packed form: tabp[j] = {c0,c1,s0,s1}, tabp[256+j] = {c2,c3,s2,s3}; a thread keeps the
+// sums of tones (0,1) and (2,3) side by side: AI01 += (x,x)*(c0,c1); AI01 += (y,y)*(s0,s1); AQ01 += (-x,-x)*(s0,s1);
+// AQ01 += (y,y)*(c0,c1) -- per tone exactly the reference's (i + x*c) + y*s and (q - x*s) + y*c.
+constexpr int SYMS_PER_CTA = 18;                           // 162 = 9 x 18
+constexpr int LAG_WIN = SYMS_PER_CTA * SPS + SPS;          // 4864 samples cover every lag of the group
+constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 609
+constexpr int LAG_THREADS = (MAXLAGS * SYMS_PER_CTA + 31) / 32 * 32;   // 608
 
-__global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
-                                                           const Job *__restrict__ jobs, const int *__restrict__ job_list,
-                                                           float4 *__restrict__ P0, int np, int stride, int lagstep,
-                                                           int nlags) {
+// threads 0..3 run the phasor recurrences (:174-188), one tone each.  Caller synchronises.
+__device__ __forceinline__ void build_tables(float fp, float4 *tab, int t) {
+    if (t < 4) {
+        float cd[4], sd[4];
+        tone_seeds(fp, cd, sd);
+        const float cdt = cd[t], sdt = sd[t];
+        float *base = reinterpret_cast<float *>(tab) + (t >> 1) * (SPS * 4) + (t & 1);
+        float c = 1.0f, s = 0.0f;
+        for (int j = 0; j < SPS; j++) {
+            base[j * 4] = c;
+            base[j * 4 + 2] = s;
+            float cn = c * cdt - s * sdt;
+            float sn = c * sdt + s * cdt;
+            c = cn;
+            s = sn;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LAG_THREADS, 2) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
+                                                              const Job *__restrict__ jobs, const int *__restrict__ job_list,
+                                                              float4 *__restrict__ P0, int np, int stride, int lagstep,
+                                                              int nlags, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float2 win[8 * LAG_PITCH];
     const Job &job = jobs[job_list[blockIdx.x]];
-    const int g = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = blockIdx.y, t = threadIdx.x;
     const float f0 = job.freq, drift = job.drift;
     const int lagmin = job.shift - 128;
     const bool shared_tab = (drift == 0.0f);
@@ -487,33 +519,36 @@ __global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restri
     if (shared_tab) build_tables(f0, tab, t);
     __syncthreads();
 
-    int sym_local, lagidx;
-    if (warp < SYMS_PER_CTA) {
-        sym_local = warp;
-        lagidx = lane;
-    } else {
-        sym_local = lane;
-        lagidx = 32;
-    }
+    const int sym_local = t / nlags, lagidx = t - sym_local * nlags;
     const int sym = g * SYMS_PER_CTA + sym_local;
-    if (sym_local >= SYMS_PER_CTA || sym >= NSYM || lagidx >= nlags) return;
+    if (sym_local >= SYMS_PER_CTA || sym >= NSYM) return;
     const int off = lagidx * lagstep + sym_local * SPS;     // window-relative start of this cell (multiple of 8)
     const float2 *wp = win + (off >> 3);
-    Acc8 a;
-#pragma unroll
-    for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
+    float4 power;
     if (shared_tab) {
+        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
 #pragma unroll 2
         for (int j8 = 0; j8 < SPS / 8; j8++) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 v = wp[r * LAG_PITCH + j8];
-                float4 w01 = tab[j8 * 8 + r], w23 = tab[SPS + j8 * 8 + r];
-                float c[4] = {w01.x, w01.z, w23.x, w23.z}, s[4] = {w01.y, w01.w, w23.y, w23.w};
-                acc_step(a, v.x, v.y, c, s);
+                const float2 v = wp[r * LAG_PITCH + j8];
+                const pk2 x = pk_make(v.x, v.x), y = pk_make(v.y, v.y), n = pk_make(-v.x, -v.x);
+                const ulonglong2 w01 = tp[j8 * 8 + r], w23 = tp[SPS + j8 * 8 + r];   // .x = (c,c'), .y = (s,s')
+                ai01 = pk_add(pk_add(ai01, pk_mul(x, w01.x, negzero), one), pk_mul(y, w01.y, negzero), one);
+                aq01 = pk_add(pk_add(aq01, pk_mul(n, w01.y, negzero), one), pk_mul(y, w01.x, negzero), one);
+                ai23 = pk_add(pk_add(ai23, pk_mul(x, w23.x, negzero), one), pk_mul(y, w23.y, negzero), one);
+                aq23 = pk_add(pk_add(aq23, pk_mul(n, w23.y, negzero), one), pk_mul(y, w23.x, negzero), one);
             }
         }
+        Acc8 a;
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
+        power = acc_power(a);
     } else {
+        Acc8 a;
+#pragma unroll
+        for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
         float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         tone_seeds(symbol_freq(f0, drift, sym), cd, sd);
         for (int j8 = 0; j8 < SPS / 8; j8++) {
@@ -530,8 +565,9 @@ __global__ void __launch_bounds__(LAG_THREADS) k_sync_lags(const float *__restri
                 }
             }
         }
+        power = acc_power(a);
     }
-    P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = acc_power(a);
+    P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = power;
 }
 
 // per-lag sync metric and arg-max over lags (:216-218,227-232); one warp-sized CTA per job
@@ -576,7 +612,7 @@ void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_
                       const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
     k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, job_list, P0, p.np, p.stride,
-                                                                          p.lagstep, p.nlags);
+                                                                          p.lagstep, p.nlags, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_lag<<<njobs, 64, 0, st>>>(jobs, job_list, P0, p.lagstep, p.nlags);
     LAUNCHED();
@@ -584,26 +620,34 @@ void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_
 
 // ---- one symbol per thread at a fixed lag (modes 1 and 2, and the generic ABI wrapper) ----------------------
 __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip, const float *__restrict__ qp, int np,
-                                                   int start, bool shared_tab, const float4 *tab, float fp) {
+                                                   int start, bool shared_tab, const float4 *tab, float fp, pk2 negzero,
+                                                   pk2 one) {
     Acc8 a;
 #pragma unroll
     for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
     const bool inside = (start > 0) && (start + SPS <= np);
     float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (!shared_tab) tone_seeds(fp, cd, sd);
-    if (shared_tab && inside && ((start & 3) == 0)) {
+    if (shared_tab && inside && ((start & 3) == 0)) {          // the common case, packed like k_sync_lags
         const float4 *i4 = reinterpret_cast<const float4 *>(ip + start), *q4 = reinterpret_cast<const float4 *>(qp + start);
+        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
 #pragma unroll 2
         for (int j4 = 0; j4 < SPS / 4; j4++) {
             float4 xi = i4[j4], xq = q4[j4];
             float xs[4] = {xi.x, xi.y, xi.z, xi.w}, ys[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                float4 w01 = tab[j4 * 4 + r], w23 = tab[SPS + j4 * 4 + r];
-                float cc[4] = {w01.x, w01.z, w23.x, w23.z}, ss[4] = {w01.y, w01.w, w23.y, w23.w};
-                acc_step(a, xs[r], ys[r], cc, ss);
+                const pk2 x = pk_make(xs[r], xs[r]), y = pk_make(ys[r], ys[r]), n = pk_make(-xs[r], -xs[r]);
+                const ulonglong2 w01 = tp[j4 * 4 + r], w23 = tp[SPS + j4 * 4 + r];
+                ai01 = pk_add(pk_add(ai01, pk_mul(x, w01.x, negzero), one), pk_mul(y, w01.y, negzero), one);
+                aq01 = pk_add(pk_add(aq01, pk_mul(n, w01.y, negzero), one), pk_mul(y, w01.x, negzero), one);
+                ai23 = pk_add(pk_add(ai23, pk_mul(x, w23.x, negzero), one), pk_mul(y, w23.y, negzero), one);
+                aq23 = pk_add(pk_add(aq23, pk_mul(n, w23.y, negzero), one), pk_mul(y, w23.x, negzero), one);
             }
         }
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
     } else {
         for (int j = 0; j < SPS; j++) {
             int k = start + j;
@@ -614,7 +658,7 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
             }
             if (shared_tab) {
                 float4 w01 = tab[j], w23 = tab[SPS + j];
-                float cc[4] = {w01.x, w01.z, w23.x, w23.z}, ss[4] = {w01.y, w01.w, w23.y, w23.w};
+                float cc[4] = {w01.x, w01.y, w23.x, w23.y}, ss[4] = {w01.z, w01.w, w23.z, w23.w};
                 acc_step(a, x, y, cc, ss);
             } else {
                 acc_step(a, x, y, c, s);
@@ -635,7 +679,7 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
 __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I, const float *__restrict__ Q,
                                                     const Job *__restrict__ jobs, const int *__restrict__ job_list,
                                                     const float4 *__restrict__ P0, float4 *__restrict__ P1, int np,
-                                                    int stride) {
+                                                    int stride, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     const Job &job = jobs[job_list[blockIdx.x]];
     const int fi = blockIdx.y, t = threadIdx.x;
@@ -652,7 +696,7 @@ __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I,
     if (t >= NSYM) return;
     const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
     float fp = shared_tab ? f0 : symbol_freq(f0, job.drift, t);
-    P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = correlate_symbol(ip, qp, np, job.shift + t * SPS, shared_tab, tab, fp);
+    P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = correlate_symbol(ip, qp, np, job.shift + t * SPS, shared_tab, tab, fp, negzero, one);
 }
 
 // soft symbols from the four tone magnitudes of one (frequency, lag) (:216-225,243-256) followed by the caller's
@@ -756,7 +800,7 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_
 void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, const float4 *P0, float4 *P1,
                        Attempt *att0, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, p.np, p.stride);
+    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
     LAUNCHED();
@@ -851,7 +895,7 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
                                                      const Job *__restrict__ jobs, const Attempt *__restrict__ att0,
                                                      const int *__restrict__ defer_list, ChainScratch *__restrict__ scratch,
-                                                     int np, int stride, float minrms, int symfac) {
+                                                     int np, int stride, float minrms, int symfac, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float4 P[NSYM];
     const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
@@ -877,7 +921,7 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
     if (t < NSYM) {
         const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
         const float fp = shared_tab ? job.freq : symbol_freq(job.freq, job.drift, t);
-        P[t] = correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp);
+        P[t] = correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp, negzero, one);
     }
     __syncthreads();
     if (t == 0) {
@@ -948,7 +992,8 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, C
     if (n <= 0) return;
     fano_attrs();
     const int nattempts = p.quickmode ? 1 : NJIT;
-    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac);
+    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac, PK_NEGZERO,
+                                                      PK_ONE);
     LAUNCHED();
     const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
     // WSPR_DEBUG_CHAIN_MAXCYCLES: experiment knob (wrong results!) to measure what the long Fano runs cost
@@ -1015,7 +1060,7 @@ __global__ void k_resolve(Job *__restrict__ jobs, CapState *__restrict__ caps, S
     const int cap = res_list[e];
     CapState &cs = caps[cap];
     cs.sub_pending = 0;
-    ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP};
+    ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP, p.preload};
     const Job &job = jobs[cap];
     for (int once = 0; once < 1; once++) {                    // (the reference's `continue` / `break` targets)
         if (!(job.worth && job.decoded)) continue;
@@ -1160,8 +1205,9 @@ constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
 __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, float *__restrict__ Q,
                                                          const CapState *__restrict__ caps, const int *__restrict__ sublist,
                                                          const Counters *cnt, const float2 *__restrict__ ref,
-                                                         const float2 *__restrict__ cprod, int np, int stride) {
-    __shared__ float2 sc[LPF_R * LPF_PITCH];
+                                                         const float2 *__restrict__ cprod, int np, int stride, pk2 negzero,
+                                                         pk2 one) {
+    __shared__ __align__(8) float2 sc[LPF_R * LPF_PITCH];
     const int s = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
     if (s >= cnt->nsub) return;
     const int cap = sublist[s];
@@ -1174,28 +1220,33 @@ __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, 
         sc[(m % LPF_R) * LPF_PITCH + m / LPF_R] = (g < CPAD) ? src[m] : make_float2(0.0f, 0.0f);
     }
     __syncthreads();
-    float ai[LPF_R], aq[LPF_R];
-    float2 w[LPF_R];                                         // sliding window: inputs 4t+tap .. 4t+tap+3
+    pk2 acc[LPF_R];                                          // (i, q) sums side by side (packed pairs, see pk_mul/pk_add)
+    pk2 w[LPF_R];                                            // sliding window: inputs 4t+tap .. 4t+tap+3
+    const pk2 *scp = reinterpret_cast<const pk2 *>(sc);
 #pragma unroll
     for (int r = 0; r < LPF_R; r++) {
-        ai[r] = aq[r] = 0.0f;
-        w[r] = sc[r * LPF_PITCH + t];
+        acc[r] = 0;
+        w[r] = scp[r * LPF_PITCH + t];
     }
     for (int tap = 0; tap < NFILT; tap += LPF_R) {
 #pragma unroll
         for (int u = 0; u < LPF_R; u++) {
             const float wt = c_lpf_w[tap + u];
+            const pk2 wt2 = pk_make(wt, wt);
             // at tap+u the window holds inputs (4t + tap+u + r); rotate by u
 #pragma unroll
-            for (int r = 0; r < LPF_R; r++) {
-                float2 v = w[(u + r) % LPF_R];
-                ai[r] = ai[r] + wt * v.x;                      // :388-389
-                aq[r] = aq[r] + wt * v.y;
-            }
+            for (int r = 0; r < LPF_R; r++)                   // :388-389  i += w*c.x ; q += w*c.y
+                acc[r] = pk_add(acc[r], pk_mul(wt2, w[(u + r) % LPF_R], negzero), one);
             // slot u now leaves the window; refill it with input 4t + tap+u + 4
             int m = LPF_R * t + tap + u + LPF_R;
-            w[u] = sc[(m % LPF_R) * LPF_PITCH + m / LPF_R];
+            w[u] = scp[(m % LPF_R) * LPF_PITCH + m / LPF_R];
         }
+    }
+    float ai[LPF_R], aq[LPF_R];
+#pragma unroll
+    for (int r = 0; r < LPF_R; r++) {
+        ai[r] = pk_lo(acc[r]);
+        aq[r] = pk_hi(acc[r]);
     }
 #pragma unroll
     for (int r = 0; r < LPF_R; r++) {                         // :397-410
@@ -1224,7 +1275,7 @@ void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublis
     k_sub_ref<<<dim3(nsub_max, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
     k_sub_lpf<<<dim3(nsub_max, (NSIG + LPF_TILE - 1) / LPF_TILE), LPF_THREADS, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod,
-                                                                                        p.np, p.stride);
+                                                                                        p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
 
@@ -1307,7 +1358,7 @@ void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStrea
 // =========================================================================================================
 __global__ void __launch_bounds__(192) k_sync_generic(const float *__restrict__ I, const float *__restrict__ Q, int np,
                                                       float freq, int ifmin, float fstep, int lagmin, int lagstep,
-                                                      float drift, float4 *__restrict__ P) {
+                                                      float drift, float4 *__restrict__ P, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     const int l = blockIdx.x, fi = blockIdx.y, t = threadIdx.x;
     const float f0 = freq + (float)(ifmin + fi) * fstep;
@@ -1316,13 +1367,13 @@ __global__ void __launch_bounds__(192) k_sync_generic(const float *__restrict__ 
     __syncthreads();
     if (t >= NSYM) return;
     float fp = shared_tab ? f0 : symbol_freq(f0, drift, t);
-    P[((size_t)fi * gridDim.x + l) * NSYM + t] = correlate_symbol(I, Q, np, lagmin + l * lagstep + t * SPS, shared_tab, tab, fp);
+    P[((size_t)fi * gridDim.x + l) * NSYM + t] = correlate_symbol(I, Q, np, lagmin + l * lagstep + t * SPS, shared_tab, tab, fp, negzero, one);
 }
 void launch_sync_generic(const float *I, const float *Q, int np, float freq, int ifmin, int ifmax, float fstep, int lagmin,
                          int lagmax, int lagstep, float drift, float4 *P, cudaStream_t st) {
     int nf = ifmax - ifmin + 1, nl = (lagmax - lagmin) / lagstep + 1;
     if (nf <= 0 || nl <= 0) return;
-    k_sync_generic<<<dim3(nl, nf), 192, 0, st>>>(I, Q, np, freq, ifmin, fstep, lagmin, lagstep, drift, P);
+    k_sync_generic<<<dim3(nl, nf), 192, 0, st>>>(I, Q, np, freq, ifmin, fstep, lagmin, lagstep, drift, P, PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
 

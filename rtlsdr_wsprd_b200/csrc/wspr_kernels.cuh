@@ -53,6 +53,7 @@ struct DecodeParams {
     int lagstep;        // 8, or 16 in quick mode
     int nlags;          // 33 / 17
     unsigned fano_budget;   // cycles a jitter-0 Fano attempt may spend inside a round before it is deferred
+    const char *preload;    // device [32768][13]: callsign hash table loaded from hashtable.txt (options.usehashtable), or null
 };
 // wsprd.c:524-531
 __host__ __device__ inline int pass_maxdrift(int ipass) { return ipass == 2 ? 0 : 4; }

@@ -48,3 +48,32 @@ def diff_results(a, b):
 
 def spot_lines(r):
     return [po.spot_line(x) for x in r]
+
+
+def hashtable_scenario():
+    """Three captures for the persistent-hashtable option (reference -H, wsprd.c:481-494,842-852): A teaches the table a
+    type-1 and a type-2 callsign, B refers to them (and to an unknown one) by hash in type-3 messages, then A again."""
+    def cap(idx, msgs):
+        sig = [dict(message=m, f0=-80.0 + 35.0 * k, dt0=0.1 * k, snr=-12.0) for k, m in enumerate(msgs)]
+        return corpus.make_capture(77, idx, sig, channel_symbols)
+    a = cap(0, ["K1JT FN20 20", "PJ4/K1ABC 37", "W1AW FN31 30"])
+    b = cap(1, ["<PJ4/K1ABC> FK52UD 37", "<K1JT> FN20AB 20", "<G4JNT> IO90AA 23", "VA2GKA FN35 10"])
+    return [a, b, a]
+
+
+def run_hashtable_scenario(decode_one, seed_file=None):
+    """decode_one(i, q) -> results, called in a fresh scratch CWD; returns [(results, hashtable.txt text)] per capture."""
+    import tempfile
+    out, old = [], os.getcwd()
+    with tempfile.TemporaryDirectory(prefix="wspr_ht_") as d:
+        os.chdir(d)
+        try:
+            if seed_file is not None:
+                with open("hashtable.txt", "w") as f:
+                    f.write(seed_file)
+            for i, q in hashtable_scenario():
+                r = decode_one(i.copy(), q.copy())
+                out.append((r, open("hashtable.txt").read()))
+        finally:
+            os.chdir(old)
+    return out

@@ -203,3 +203,30 @@ def test_reference_unit_tests_link_against_our_library(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     assert "18" in out.stdout
+
+
+def test_packed_products_and_sums_are_not_contracted():
+    """The correlation / low-pass kernels issue their exact-order multiplies and adds as FFMA2 pairs (a*b + -0.0, then
+    a*1.0 + c).  ptxas contracts such a pair into one fused multiply-add whenever it can see the two constants (it does
+    so even under -fmad=false), which would change roundings, so the constants are run-time kernel arguments.  Check the
+    SASS of the built library: each kernel must hold TWO FFMA2 per packed multiply-accumulate of its unrolled inner loop
+    (a contracted build would show half as many).  The GPU parity tests are the functional check of the same thing."""
+    lib = w.library_path()
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("cuobjdump not available")
+    count, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+        elif cur and "FFMA2" in line:
+            count[cur] = count.get(cur, 0) + 1
+    # packed multiply-accumulates per sample (4 tones x {i,q} x 2 products / 2 lanes = 8; low-pass: 4 outputs) x samples
+    # (taps) in the unrolled loop body x 2 instructions each
+    expected = {"k_sync_lags": 8 * 16 * 2, "k_sync_freqs": 8 * 8 * 2, "k_jitter_soft": 8 * 8 * 2, "k_sync_generic": 8 * 8 * 2,
+                "k_sub_lpf": 4 * 8 * 2}
+    for name, n in expected.items():
+        got = sum(v for k, v in count.items() if name in k)
+        assert got == n, (name, got, n)

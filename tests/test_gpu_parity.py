@@ -285,6 +285,23 @@ def test_option_variants_on_weak_signals(opt):
     assert_batch_equals_oracle(I, Q, **opt)
 
 
+def test_persistent_hashtable_option():
+    """options.usehashtable (reference -H, wsprd.c:481-494,842-852) through the reference entry point: spots and the
+    hashtable.txt left in the CWD after every call identical to the oracle's."""
+    opt_o, opt_g = po.default_options(usehashtable=1), w.default_options(usehashtable=1)
+    seed = "   17 ZZ9ZZZ AA00\n40000 BAD\n  junk\n 5970 OLDCALL\n"
+    want = H.run_hashtable_scenario(lambda i, q: po.decode(po.oracle(), i, q, opt_o, cwd_scratch=False)[0], seed)
+    got = H.run_hashtable_scenario(lambda i, q: w.wspr_decode(i, q, options=opt_g), seed)
+    assert any(b"<K1JT>" in x["message"] for x in got[1][0]) and any(b"<...>" in x["message"] for x in got[1][0])
+    for (ra, fa), (rb, fb) in zip(want, got):
+        assert H.results_equal(ra, rb), H.diff_results(ra, rb)
+        assert fa == fb, (fa, fb)
+    # without the option nothing is read or written and hashed calls stay unresolved
+    i, q = H.hashtable_scenario()[1]
+    r = w.wspr_decode(i.copy(), q.copy())
+    assert not any(b"<K1JT>" in x["message"] for x in r) and any(b"<...>" in x["message"] for x in r)
+
+
 def test_fano_kernel_against_oracle_random_vectors():
     """K5 alone: random soft-symbol vectors from clean to hopeless, both storage variants of the device decoder, against
     fano() of the oracle (return code, metric, cycle count, deepest node, decoded bytes); timeouts at a reduced maxcycles

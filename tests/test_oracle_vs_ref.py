@@ -183,3 +183,21 @@ def test_oracle_frontend_equals_reference_callback():
     n = orc.oracle_decimate(raw.ctypes.data, n_iq, io.ctypes.data, qo.ctypes.data, 64)
     assert n == len(ir) == 40
     assert np.array_equal(io[:n], ir) and np.array_equal(qo[:n], qr)
+
+
+def test_persistent_hashtable_option_matches_reference():
+    """options.usehashtable (reference -H): hashed callsigns of type-3 messages resolve through hashtable.txt carried
+    from one call to the next; results and the file after every call are identical between oracle and reference."""
+    if not po.ref_available():
+        pytest.skip("compiled reference not available")
+    opt = po.default_options(usehashtable=1)
+    seed = "   17 ZZ9ZZZ AA00\n40000 BAD\n  junk\n 5970 OLDCALL\n"      # existing entries, an out-of-range one, garbage
+    runs = {}
+    for name, lib in (("ref", po.ref()), ("oracle", po.oracle())):
+        runs[name] = H.run_hashtable_scenario(lambda i, q: po.decode(lib, i, q, opt, cwd_scratch=False)[0], seed)
+    msgs = [[x["message"].decode() for x in r] for r, _ in runs["ref"]]
+    assert "<K1JT> FN20AB 20" in msgs[1] and "<PJ4/K1ABC> FK52UD 37" in msgs[1] and "<...> IO90AA 23" in msgs[1], msgs
+    for (ra, fa), (rb, fb) in zip(runs["ref"], runs["oracle"]):
+        assert H.results_equal(ra, rb), H.diff_results(ra, rb)
+        assert fa == fb
+    assert "   17 ZZ9ZZZ AA00" in runs["ref"][0][1] and " 5970 W1AW FN31" in runs["ref"][0][1]
