@@ -138,7 +138,9 @@ double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
 
 /* the Fano decoder kernel (K5) on caller-supplied soft symbols: n vectors of 162 deinterleaved bytes, the batch / device
  * counterpart of fano() (wsprd/fano.h:14-28; metric table = the one wspr_decode builds, wsprd.c:467-473).  stop_after != 0
- * cuts a run short after that many cycles (rc 2); solo != 0 runs one attempt per warp (the shape used for long runs).
+ * cuts a run short after that many cycles (rc 2); solo bit 0: one attempt per warp instead of 32; bit 1: tree state in global
+ * memory; bit 2: the instantiation the decode kernels use (time-out test every 256 trips, maxnp not tracked: rc, cycles and
+ * data as fano.c's, metric too for successful decodes).
  * rc/metric/cycles/maxnp: n entries each, data: n x 12 bytes (host memory); clocks (may be NULL): SM clock ticks each
  * attempt took. */
 int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
@@ -160,6 +162,30 @@ int wspr_decimate_device(const uint8_t *d_raw, int nstreams, size_t n_iq, size_t
 /* device time (ms, CUDA events) of the kernels of the last wspr_decimate_device call; text of the last front-end error */
 float wspr_decimate_last_ms(void);
 const char *wspr_frontend_last_error(void);
+
+
+/* ---- streaming form: what the live daemon's receive thread and main loop do ----
+ * A front-end context owns, for `nstreams` receivers advancing in lockstep, the filter state rtlsdr_callback keeps in
+ * function statics (integrators, decimation phase, comb delay lines, FIR history: rtlsdr_wsprd.c:130-136,155-156; zero at
+ * creation, never reset afterwards) and the reference's double buffer of `slot_samples` outputs (rx_state.iSamples /
+ * qSamples / iqIndex / bufferIndex, rtlsdr_wsprd.c:80-87; 0 selects 45000). */
+typedef struct wspr_frontend wspr_frontend;
+wspr_frontend *wspr_frontend_create(int device, int nstreams, int slot_samples);
+void wspr_frontend_destroy(wspr_frontend *fe);
+/* rtlsdr_callback(samples, samples_count, ctx) (rtlsdr_wsprd.c:126) for every stream: raw + s * stream_stride_bytes holds
+ * nbytes interleaved u8 (I,Q) bytes of stream s (host memory, not modified; nbytes must be a multiple of 8 as the
+ * reference's mixer loop assumes, :171).  Outputs beyond slot_samples are dropped but still advance the filters (:238).
+ * Returns the number of outputs produced per stream, or a negative error. */
+int wspr_frontend_push(wspr_frontend *fe, const uint8_t *raw, size_t stream_stride_bytes, uint32_t nbytes);
+/* outputs held by the slot being filled (rx_state.iqIndex[bufferIndex]) */
+int wspr_frontend_samples(wspr_frontend *fe);
+/* the main loop's slot switch (rtlsdr_wsprd.c:1181-1183): the other buffer becomes current and starts empty.  Returns the
+ * number of samples in the slot that just ended; its tail is zeroed like decoder() does (rtlsdr_wsprd.c:285-288). */
+int wspr_frontend_swap(wspr_frontend *fe);
+/* the slot that ended at the last swap: host copy ([nstreams][slot_samples] floats each) / device pointers (row stride in
+ * floats) to hand to wspr_ctx_upload_device + wspr_ctx_normalise.  Both return the samples the slot holds. */
+int wspr_frontend_read(wspr_frontend *fe, float *I, float *Q);
+int wspr_frontend_slot_device(wspr_frontend *fe, const float **dI, const float **dQ, int *stride);
 
 #ifdef __cplusplus
 }

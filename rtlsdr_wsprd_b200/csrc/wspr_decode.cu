@@ -146,6 +146,8 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     c->np = samples;
     c->stride = (samples + 127) / 128 * 128;
     c->blocks = 4 * (samples / NFFT) - 1;                    // wsprd.c:516
+    // (Stream priorities were tried -- main stream highest, side streams lowest, so that pending bulk blocks are dispatched
+    // ahead of pending chain blocks: 2 % slower end to end, and a background Fano grid still serialises a decode behind it.)
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -653,6 +655,36 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     if (e != cudaSuccess) ret = fail(WSPR_ERR_CUDA, "wspr_fano_batch", e);
     cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k); cudaFree(d_g);
     return ret;
+}
+
+// Experiment hook (tools/exp_interference.py): put `nctas` one-warp Fano CTAs of hopeless attempts (the shape of k_chain_fano)
+// in flight on a private stream and return at once; wspr_debug_fano_load(0, 0) waits for them.  Not part of the product path.
+extern "C" int wspr_debug_fano_load(int nctas, unsigned maxcycles) {
+    static cudaStream_t st = nullptr;
+    static unsigned char *d_sym = nullptr;
+    static int *d_i = nullptr;
+    static unsigned *d_u = nullptr;
+    static unsigned char *d_data = nullptr;
+    const int cap = 1024 * 32;
+    if (!st) {
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaMalloc((void **)&d_sym, (size_t)cap * NSYM));
+        CK(cudaMalloc((void **)&d_i, (size_t)cap * sizeof(int)));
+        CK(cudaMalloc((void **)&d_u, (size_t)3 * cap * sizeof(unsigned)));
+        CK(cudaMalloc((void **)&d_data, (size_t)cap * 12));
+        std::vector<unsigned char> h((size_t)cap * NSYM);
+        unsigned x = 12345u;
+        for (auto &b : h) { x = x * 1664525u + 1013904223u; b = (unsigned char)(x >> 24); }
+        CK(cudaMemcpy(d_sym, h.data(), h.size(), cudaMemcpyHostToDevice));
+    }
+    if (nctas <= 0) {
+        CK(cudaStreamSynchronize(st));
+        return WSPR_OK;
+    }
+    const int n = std::min(nctas * 32, cap);
+    launch_fano_test(d_sym, n, 60, maxcycles, 0, 0, d_i, d_u, d_u + cap, d_u + 2 * cap, d_data, nullptr, nullptr, st);
+    CK(cudaGetLastError());
+    return WSPR_OK;
 }
 
 // sync_and_demodulate: correlation grid on the GPU, the handful of scalar reductions on the host in the

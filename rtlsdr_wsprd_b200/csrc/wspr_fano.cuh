@@ -54,6 +54,13 @@ __device__ __forceinline__ void sts128(unsigned addr, unsigned x, unsigned y, un
 // warp, 256 when only the first 16 lanes decode (the scratch is then half the size).
 struct FanoSmem {
     unsigned base, row;
+    // base: shared-state-space address of the scratch, pinned in a register (otherwise the window base of dynamic shared
+    // memory is re-derived from special registers on every loop trip)
+    static __device__ __forceinline__ FanoSmem at(const void *smem, unsigned row) {
+        unsigned b = (unsigned)__cvta_generic_to_shared(smem);
+        asm volatile("" : "+r"(b));
+        return FanoSmem{b, row};
+    }
     __device__ __forceinline__ uint4 ld(unsigned off) const { return lds128(base + off); }
     __device__ __forceinline__ void st(unsigned off, unsigned x, unsigned y, unsigned z, unsigned w) const { sts128(base + off, x, y, z, w); }
 };
@@ -83,10 +90,22 @@ struct FanoNoStop {                    // hook: stop() polled every 256 trips by
 // A lane that has finished keeps executing the (uniform) loop as a harmless zombie -- its threshold is parked so high
 // that it only ever tightens it in place -- while its result waits in separate registers; the hot loop therefore
 // carries no per-lane "active" predicate.
-template <typename Hook, typename Mem>
-__device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
-                                           const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
-                                           Hook hook, Mem mem) {
+//
+// The throughput of the whole decode is very sensitive to the length of one trip (a hopeless candidate keeps 43 lanes
+// busy for 810 000 cycles, and the SMs they sit on are shared with the bulk kernels), so the loop body is kept minimal:
+//   * `w` carries the node's packed branch metrics AND, in bit 31, which branch is being tried (sel); the record a node
+//     is left with is stored and reloaded in that form, no packing or unpacking;
+//   * the metric of the branch being tried (`cur`) is extracted at the end of the previous trip, off the critical path;
+//   * EXACT = false (the decode kernels): the time-out test is made every 256 trips instead of every trip -- a lane past
+//     the limit can no longer succeed (the decode test checks the count) and walks on harmlessly until it is noticed --
+//     and maxnp, which wspr_decode never looks at, is not tracked.  `cycles` of a time-out is the reference's constant
+//     either way; only `metric` of a time-out (unused by wspr_decode, fano.c:236) is then not the reference's.
+//     EXACT = true (fano() parity tests): every output field as fano.c produces it.
+//   * SMALLSTEP: delta > 10; a branch metric is at most +10, so one threshold step per move suffices.
+template <bool EXACT, bool SMALLSTEP, typename Hook, typename Mem>
+__device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
+                                                const short *__restrict__ mettab, int delta, unsigned maxcycles,
+                                                unsigned stop_after, Hook hook, Mem mem) {
     constexpr int nbits = NBITS;
     constexpr int tail = nbits - 31;
     constexpr int PARKED = 0x3fffffff;
@@ -115,19 +134,26 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
     for (int n = 0; n < FANO_NODE_RECORDS; n++) mem.st(node_base + row * (unsigned)n, 0u, 0u, 0u, 0u);
     const unsigned limit = maxcycles * (unsigned)nbits;
     const unsigned stop = (stop_after != 0 && stop_after < limit) ? stop_after : 0xffffffffu;
-    const bool smallstep = delta > 10;             // a branch metric is at most +10: one threshold step per move suffices
     const float inv_delta = 1.0f / (float)delta;
 
     bool act = want, inback = false;
-    int pos = 0, thr = want ? 0 : PARKED, gam = 0, pgam = 0, sel = 0, maxnp = 0;
+    int pos = 0, thr = want ? 0 : PARKED, gam = 0, pgam = 0, maxnp = 0;
     unsigned it = 0;                               // Fano cycles started so far
-    unsigned w = mem.ld(lvl_base).x;               // root: branch_sym(0) == 0
+    unsigned w = mem.ld(lvl_base).x;               // root: branch_sym(0) == 0; bit 31 (sel) = 0: the better branch first
     unsigned enc = w >> 30;
+    int cur = fano_tm0(w);                         // metric of the branch being tried
     int r_rc = -1;                                 // result registers, filled when the lane finishes
     unsigned r_metric = 0, r_cycles = 0, r_maxnp = 0;
 #pragma unroll 1
     for (unsigned trip = 0;; trip++) {
         if ((trip & 255u) == 0u) {                 // housekeeping
+            if (!EXACT && act && it >= limit) {    // the reference's loop ended somewhere in the last 256 trips: time-out
+                act = false;
+                r_rc = -1;
+                r_metric = (unsigned)gam;
+                r_cycles = limit + 2u;
+                r_maxnp = 0u;
+            }
             if (act && !inback && (it >= stop || hook.stop())) {
                 act = false;
                 r_rc = FANO_STOPPED;
@@ -138,15 +164,16 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
             }
             if (!__any_sync(0xffffffffu, act)) break;
         }
-        // speculative fetches: the level we would move down to, the node we would step back to
+        // speculative fetches: the level we would move down to, the node we would step back to (never used at the root,
+        // where the address below is the last level record)
         const uint4 nl = mem.ld(lvl_base + row * (unsigned)(pos + 1));
-        const uint4 nd = mem.ld(node_base + row * (unsigned)max(pos - 1, 0));
-        const int ng = gam + (sel ? fano_tm1(w) : fano_tm0(w));
+        const uint4 nd = mem.ld(node_base + row * (unsigned)pos - row);
+        const int ng = gam + cur;
         const bool newc = !inback;                 // this trip opens a new Fano cycle
         const bool fwd = newc && (ng >= thr);
         const bool tig = newc && !fwd && (pos == 0 || pgam < thr);
         const bool bck = !fwd && !tig;
-        if (newc && it >= limit && act) {           // the reference's loop ends here: time-out (rare, once per lane)
+        if (EXACT && newc && it >= limit && act) {  // the reference's loop ends here: time-out (rare, once per lane)
             act = false;
             r_rc = -1;
             r_metric = (unsigned)gam;
@@ -154,11 +181,12 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
             r_maxnp = (unsigned)maxnp;
         }
         it += newc ? 1u : 0u;
-        maxnp = newc ? max(maxnp, pos) : maxnp;
+        if (EXACT) maxnp = newc ? max(maxnp, pos) : maxnp;
         // ---- forward: raise the threshold on a first visit, push the node, descend along the better branch
         int thrF = thr;
-        if (smallstep) {
-            thrF = (gam < thr + delta && ng >= thr + delta) ? thr + delta : thr;
+        if (SMALLSTEP) {
+            const int t1 = thr + delta;
+            thrF = (gam < t1 && ng >= t1) ? t1 : thr;
         } else if (gam < thr + delta) {             // while (ng >= thr + delta) thr += delta
             const int d = ng - thr;
             int k = __float2int_rz((float)d * inv_delta);
@@ -166,27 +194,29 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
             k -= (k * delta > d) ? 1 : 0;
             thrF = thr + k * delta;
         }
-        if (fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w | ((unsigned)sel << 31), (unsigned)pgam);
+        if (fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w, (unsigned)pgam);
         const unsigned e = enc << 1;
-        const unsigned pa = __popc(e & POLY_A) & 1u, pb = __popc(e & POLY_B) & 1u;   // branch symbol = 2*pa + pb
+        const bool pa = (__popc(e & POLY_A) & 1) != 0, pb = (__popc(e & POLY_B) & 1) != 0;   // branch symbol = 2*pa + pb
         const unsigned wlo = pb ? nl.y : nl.x, whi = pb ? nl.w : nl.z;
-        const unsigned wF = pa ? whi : wlo;
+        const unsigned wF = pa ? whi : wlo;          // (bit 31 clear: the better branch first)
         const unsigned encF = e | (wF >> 30);
         // ---- step back onto the parent
-        const unsigned encB0 = nd.x, wB = nd.z & 0x7fffffffu;
-        const int selB0 = (int)(nd.z >> 31), pgamB = (int)nd.w;
-        const bool b1 = (pos - 1 < tail) && (selB0 == 0);            // take the parent's other branch
-        const bool b2 = !b1 && (pos - 1 == 0 || pgamB < thr);        // cannot go higher: tighten there
-        const unsigned encB = encB0 ^ (unsigned)(b1 ? 1 : (b2 ? selB0 : 0));
-        const int selB = b1 ? 1 : (b2 ? 0 : selB0);
+        const unsigned wB0 = nd.z;
+        const bool selB0 = (int)wB0 < 0;
+        const int pgamB = (int)nd.w;
+        const bool b1 = (pos <= tail) && !selB0;                     // take the parent's other branch
+        const bool b2 = !b1 && (pos == 1 || pgamB < thr);            // cannot go higher: tighten there
+        const unsigned wB = b1 ? (wB0 | 0x80000000u) : (b2 ? (wB0 & 0x7fffffffu) : wB0);
+        const unsigned encB = nd.x ^ ((b1 || (b2 && selB0)) ? 1u : 0u);
         // ---- merge
         const int dthr = (tig || (bck && b2)) ? delta : 0;
         thr = fwd ? thrF : thr - dthr;
+        const int gamN = fwd ? ng : (bck ? pgam : gam);              // (the parent's path metric is what pgam holds)
         pgam = fwd ? gam : (bck ? pgamB : pgam);
-        gam = fwd ? ng : (bck ? (int)nd.y : gam);
-        enc = fwd ? encF : (bck ? encB : (enc ^ (unsigned)sel));
-        w = fwd ? wF : (bck ? wB : w);
-        sel = fwd ? 0 : (bck ? selB : 0);
+        gam = gamN;
+        enc = fwd ? encF : (bck ? encB : (enc ^ (w >> 31)));
+        w = fwd ? wF : (bck ? wB : (w & 0x7fffffffu));
+        cur = ((int)w < 0) ? fano_tm1(w) : fano_tm0(w);
         inback = bck && !b1 && !b2;
         pos += fwd ? 1 : (bck ? -1 : 0);
         if (pos == nbits) {                        // reached the last node: decoded (rare, once per lane)
@@ -194,7 +224,7 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
                 act = false;
                 r_rc = (it >= limit) ? -1 : 0;     // (a decode in the very last cycle counts as a timeout, fano.c:234)
                 r_metric = (unsigned)gam;
-                r_cycles = it + 1u;
+                r_cycles = (it > limit) ? limit + 2u : it + 1u;   // (it > limit: a lane past the limit, not yet noticed)
                 r_maxnp = (unsigned)maxnp;
                 if (r_rc == 0) hook.success();
             }
@@ -213,6 +243,14 @@ __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const uns
 #pragma unroll
         for (int b = 0; b < (nbits >> 3); b++) out.data[b] = (unsigned char)mem.ld(node_base + row * (unsigned)(7 + 8 * b)).x;
     }
+}
+
+template <bool EXACT, typename Hook, typename Mem>
+__device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
+                                           const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
+                                           Hook hook, Mem mem) {
+    if (delta > 10) fano_dense_impl<EXACT, true>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
+    else fano_dense_impl<EXACT, false>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
 }
 
 }  // namespace wspr

@@ -133,13 +133,15 @@ constexpr int MOM_WARPS = 8;
 constexpr int MOM_UNROLL = 5;
 
 // one warp per 6401-sample block.  raw must be 16-byte aligned per stream.
+// first_byte: offset of block 0 inside each stream's buffer; the buffer's byte 0 must be sample 0 (mod 8) of the stream,
+// because the mixer phase is taken from the position inside the 16-byte vector.
 __global__ void __launch_bounds__(MOM_WARPS * 32) k_block_moments(const uint8_t *__restrict__ raw, size_t stream_stride,
-                                                                  int nblk, uint4 *__restrict__ moments) {
+                                                                  int nblk, uint4 *__restrict__ moments, int first_byte) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * MOM_WARPS + warp, stream = blockIdx.y;
     if (b >= nblk) return;
     const uint8_t *base = raw + (size_t)stream * stream_stride;
-    const long long byte0 = (long long)b * BLOCK_BYTES, byte1 = byte0 + BLOCK_BYTES;
+    const long long byte0 = (long long)first_byte + (long long)b * BLOCK_BYTES, byte1 = byte0 + BLOCK_BYTES;
     const long long v0 = byte0 >> 4, v1 = (byte1 + 15) >> 4;        // vectors [v0, v1) cover the block
     const int nvec = (int)(v1 - v0);                                 // 801 or 802
     const uint4 *vp = reinterpret_cast<const uint4 *>(base) + v0;
@@ -292,11 +294,53 @@ void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t strea
     upload_fir();
     if (nblk > 0) {
         k_block_moments<<<dim3((nblk + MOM_WARPS - 1) / MOM_WARPS, nstreams), MOM_WARPS * 32, 0, st>>>(raw, stream_stride_bytes,
-                                                                                                      nblk, (uint4 *)moments);
+                                                                                                      nblk, (uint4 *)moments, 0);
         g_frontend_launches++;
     }
     k_comb_fir<<<dim3((max_out + CF_CHUNK - 1) / CF_CHUNK, nstreams), CF_THREADS, 0, st>>>(moments, nblk, I, Q, out_stride, max_out);
     g_frontend_launches++;
+}
+
+// ---- streaming form: the filter state of rtlsdr_callback carried from push to push (rtlsdr_wsprd.c:130-136,155-156) ----
+struct FeChan {
+    uint32_t x1, x2;                 // integrators Ix1, Ix2 (wrapping)
+    uint32_t t1y, t1z, t2y, t2z;     // comb delay lines
+    float fir[FIR_TAPS];             // firI / firQ
+};
+struct FeState {
+    FeChan ch[2];
+};
+// One thread per (stream, channel) replays the per-output part of the callback for the nb blocks whose byte moments
+// k_block_moments has just produced: over one block of n = 6401 samples x2 += n*x1 + n*S0 - S1 and x1 += S0 (what the
+// sample-by-sample integrators add up to), then the two combs and the FIR exactly as the reference writes them.
+__global__ void k_stream_advance(FeState *__restrict__ state, const uint4 *__restrict__ moments, int nb, int nstreams,
+                                 float *__restrict__ I, float *__restrict__ Q, int out_stride, int out_pos, int cap) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stream = tid >> 1, ch = tid & 1;
+    if (stream >= nstreams) return;
+    FeChan c = state[stream].ch[ch];
+    float *out = (ch ? Q : I) + (size_t)stream * out_stride;
+    for (int b = 0; b < nb; b++) {
+        const uint4 m = moments[(size_t)stream * nb + b];
+        const uint32_t s0 = ch ? m.y : m.x, s1 = ch ? m.w : m.z;
+        c.x2 += (uint32_t)DECIM * c.x1 + (uint32_t)DECIM * s0 - s1;
+        c.x1 += s0;
+        const uint32_t y1 = c.x2 - c.t1z;                      // rtlsdr_wsprd.c:204-218
+        c.t1z = c.t1y;
+        c.t1y = c.x2;
+        const uint32_t y2 = y1 - c.t2z;
+        c.t2z = c.t2y;
+        c.t2y = y1;
+        float sum = 0.0f;                                      // rtlsdr_wsprd.c:221-234
+        for (int j = 0; j < FIR_TAPS; j++) {
+            sum = sum + c.fir[j] * c_fir[j];
+            if (j < FIR_TAPS - 1) c.fir[j] = c.fir[j + 1];
+        }
+        c.fir[FIR_TAPS - 1] = (float)(int32_t)y2;
+        sum = sum + c.fir[FIR_TAPS - 1] * c_fir[FIR_TAPS];
+        if (out_pos + b < cap) out[out_pos + b] = sum;         // rtlsdr_wsprd.c:237-242
+    }
+    state[stream].ch[ch] = c;
 }
 
 }  // namespace wspr
@@ -379,3 +423,197 @@ done:
     if (dQ) cudaFree(dQ);
     return rc;
 }
+
+// ================= streaming front end (the live daemon's callback + double buffer) =================
+struct wspr_frontend {
+    int device = 0, nstreams = 0, cap = 0;
+    cudaStream_t st = nullptr;
+    FeState *state = nullptr;
+    uint8_t *stage[2] = {nullptr, nullptr};     // [nstreams][stage_stride]: the unfinished block + the chunk being pushed
+    size_t stage_stride = 0;
+    int cur_stage = 0;
+    uint4 *moments = nullptr;
+    size_t moments_cap = 0;
+    float *I[2] = {nullptr, nullptr}, *Q[2] = {nullptr, nullptr};   // the reference's double buffer (rtlsdr_wsprd.c:80-87)
+    int iq_index[2] = {0, 0};
+    int buffer_index = 0;
+    unsigned long long blocks_done = 0;         // decimation blocks consumed since the stream started
+    size_t carry = 0;                           // bytes of the unfinished block waiting in the staging buffer
+};
+
+extern "C" void wspr_frontend_destroy(wspr_frontend *fe) {
+    if (!fe) return;
+    cudaSetDevice(fe->device);
+    if (fe->st) cudaStreamSynchronize(fe->st);
+    void *ptrs[] = {fe->state, fe->stage[0], fe->stage[1], fe->moments, fe->I[0], fe->I[1], fe->Q[0], fe->Q[1]};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (fe->st) cudaStreamDestroy(fe->st);
+    delete fe;
+}
+
+static int fe_init(wspr_frontend *fe, int device, int nstreams, int slot_samples) {
+    int rc = WSPR_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fe_fail(WSPR_ERR_CUDA, "no CUDA device");
+    if (device < 0) FCK(cudaGetDevice(&device));
+    FCK(cudaSetDevice(device));
+    fe->device = device;
+    fe->nstreams = nstreams;
+    fe->cap = slot_samples > 0 ? slot_samples : WSPR_CAPTURE_SAMPLES;
+    FCK(cudaStreamCreateWithFlags(&fe->st, cudaStreamNonBlocking));
+    FCK(cudaMalloc((void **)&fe->state, (size_t)nstreams * sizeof(FeState)));
+    FCK(cudaMemset(fe->state, 0, (size_t)nstreams * sizeof(FeState)));       // the reference's statics start at zero
+    for (int b = 0; b < 2; b++) {
+        FCK(cudaMalloc((void **)&fe->I[b], (size_t)nstreams * fe->cap * sizeof(float)));
+        FCK(cudaMalloc((void **)&fe->Q[b], (size_t)nstreams * fe->cap * sizeof(float)));
+        FCK(cudaMemset(fe->I[b], 0, (size_t)nstreams * fe->cap * sizeof(float)));
+        FCK(cudaMemset(fe->Q[b], 0, (size_t)nstreams * fe->cap * sizeof(float)));
+    }
+    FCK(upload_fir());
+done:
+    return rc;
+}
+
+extern "C" wspr_frontend *wspr_frontend_create(int device, int nstreams, int slot_samples) {
+    if (nstreams <= 0) {
+        fe_fail(WSPR_ERR_ARG, "wspr_frontend_create: bad arguments");
+        return nullptr;
+    }
+    wspr_frontend *fe = new wspr_frontend();
+    if (fe_init(fe, device, nstreams, slot_samples) != WSPR_OK) {
+        std::string keep = g_fe_err;
+        wspr_frontend_destroy(fe);
+        g_fe_err = keep;
+        return nullptr;
+    }
+    return fe;
+}
+
+// room for `need` bytes per stream in both staging buffers (contents of the current one are kept)
+static int fe_reserve(wspr_frontend *fe, size_t need) {
+    int rc = WSPR_OK;
+    const size_t stride = (need + 15) / 16 * 16 + 32;         // whole 16-byte vectors are read around every block
+    if (stride <= fe->stage_stride) return WSPR_OK;
+    uint8_t *nb[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; b++) {
+        FCK(cudaMalloc((void **)&nb[b], (size_t)fe->nstreams * stride));
+        FCK(cudaMemsetAsync(nb[b], 0x80, (size_t)fe->nstreams * stride, fe->st));
+    }
+    if (fe->stage[fe->cur_stage] && fe->stage_stride)
+        FCK(cudaMemcpy2DAsync(nb[fe->cur_stage], stride, fe->stage[fe->cur_stage], fe->stage_stride, fe->stage_stride,
+                              fe->nstreams, cudaMemcpyDeviceToDevice, fe->st));
+    FCK(cudaStreamSynchronize(fe->st));
+    for (int b = 0; b < 2; b++) {
+        if (fe->stage[b]) cudaFree(fe->stage[b]);
+        fe->stage[b] = nb[b];
+        nb[b] = nullptr;
+    }
+    fe->stage_stride = stride;
+done:
+    for (int b = 0; b < 2; b++)
+        if (nb[b]) cudaFree(nb[b]);
+    return rc;
+}
+
+extern "C" int wspr_frontend_push(wspr_frontend *fe, const uint8_t *raw, size_t stream_stride_bytes, uint32_t nbytes) {
+    if (!fe || (nbytes && !raw) || (nbytes & 7u) || (fe->nstreams > 1 && stream_stride_bytes < nbytes))
+        return fe_fail(WSPR_ERR_ARG, "wspr_frontend_push: bad arguments (the byte count must be a multiple of 8, rtlsdr_wsprd.c:171)");
+    if (nbytes == 0) return 0;
+    int rc = WSPR_OK;
+    FCK(cudaSetDevice(fe->device));
+    {
+        // byte offset of the unfinished block inside the stream, modulo the 16-byte vector grid (keeps the mixer phase)
+        const unsigned long long g0 = fe->blocks_done * (unsigned long long)BLOCK_BYTES;
+        const int pad = (int)(g0 & 15ull);
+        const size_t total = fe->carry + nbytes;
+        if (fe_reserve(fe, (size_t)pad + total) != WSPR_OK) return WSPR_ERR_CUDA;
+        uint8_t *cur = fe->stage[fe->cur_stage];
+        FCK(cudaMemcpy2DAsync(cur + pad + fe->carry, fe->stage_stride, raw, stream_stride_bytes, nbytes, fe->nstreams,
+                              cudaMemcpyHostToDevice, fe->st));
+        const int nb = (int)(total / BLOCK_BYTES);
+        if (nb > 0) {
+            if ((size_t)nb * fe->nstreams > fe->moments_cap) {
+                FCK(cudaStreamSynchronize(fe->st));
+                if (fe->moments) cudaFree(fe->moments);
+                fe->moments = nullptr;
+                fe->moments_cap = (size_t)nb * fe->nstreams;
+                FCK(cudaMalloc((void **)&fe->moments, fe->moments_cap * sizeof(uint4)));
+            }
+            k_block_moments<<<dim3((nb + MOM_WARPS - 1) / MOM_WARPS, fe->nstreams), MOM_WARPS * 32, 0, fe->st>>>(
+                cur, fe->stage_stride, nb, fe->moments, pad);
+            g_frontend_launches++;
+            const int buf = fe->buffer_index;
+            k_stream_advance<<<(2 * fe->nstreams + 63) / 64, 64, 0, fe->st>>>(fe->state, fe->moments, nb, fe->nstreams, fe->I[buf],
+                                                                            fe->Q[buf], fe->cap, fe->iq_index[buf], fe->cap);
+            g_frontend_launches++;
+            FCK(cudaGetLastError());
+            fe->iq_index[buf] = std::min(fe->cap, fe->iq_index[buf] + nb);
+            // the unfinished tail moves to the other staging buffer, re-aligned to the vector grid
+            const size_t left = total - (size_t)nb * BLOCK_BYTES;
+            fe->blocks_done += (unsigned long long)nb;
+            const int pad2 = (int)((fe->blocks_done * (unsigned long long)BLOCK_BYTES) & 15ull);
+            uint8_t *nxt = fe->stage[fe->cur_stage ^ 1];
+            if (left)
+                FCK(cudaMemcpy2DAsync(nxt + pad2, fe->stage_stride, cur + pad + (size_t)nb * BLOCK_BYTES, fe->stage_stride, left,
+                                      fe->nstreams, cudaMemcpyDeviceToDevice, fe->st));
+            fe->cur_stage ^= 1;
+            fe->carry = left;
+        } else {
+            fe->carry = total;
+        }
+        FCK(cudaStreamSynchronize(fe->st));       // `raw` belongs to the caller again (librtlsdr reuses its buffers)
+        rc = nb;
+    }
+done:
+    return rc;
+}
+
+// The main loop's slot switch (rtlsdr_wsprd.c:1181-1183): the other buffer becomes current and starts empty; returns the
+// number of samples in the slot that just ended, whose tail is zeroed like decoder() does (rtlsdr_wsprd.c:285-288).
+extern "C" int wspr_frontend_swap(wspr_frontend *fe) {
+    if (!fe) return fe_fail(WSPR_ERR_ARG, "null front end");
+    int rc = WSPR_OK;
+    FCK(cudaSetDevice(fe->device));
+    {
+        const int prev = fe->buffer_index, n = fe->iq_index[prev];
+        fe->buffer_index ^= 1;
+        fe->iq_index[fe->buffer_index] = 0;
+        if (n < fe->cap) {
+            FCK(cudaMemset2DAsync(fe->I[prev] + n, (size_t)fe->cap * sizeof(float), 0, (size_t)(fe->cap - n) * sizeof(float),
+                                  fe->nstreams, fe->st));
+            FCK(cudaMemset2DAsync(fe->Q[prev] + n, (size_t)fe->cap * sizeof(float), 0, (size_t)(fe->cap - n) * sizeof(float),
+                                  fe->nstreams, fe->st));
+        }
+        FCK(cudaStreamSynchronize(fe->st));
+        rc = n;
+    }
+done:
+    return rc;
+}
+
+// device pointers of the slot that ended at the last swap: [nstreams][stride] floats, zero padded
+extern "C" int wspr_frontend_slot_device(wspr_frontend *fe, const float **dI, const float **dQ, int *stride) {
+    if (!fe || !dI || !dQ || !stride) return fe_fail(WSPR_ERR_ARG, "wspr_frontend_slot_device");
+    const int prev = fe->buffer_index ^ 1;
+    *dI = fe->I[prev];
+    *dQ = fe->Q[prev];
+    *stride = fe->cap;
+    return fe->iq_index[prev];
+}
+
+// copy of that slot in host memory ([nstreams][slot_samples] each); returns the samples it holds
+extern "C" int wspr_frontend_read(wspr_frontend *fe, float *I, float *Q) {
+    if (!fe || !I || !Q) return fe_fail(WSPR_ERR_ARG, "wspr_frontend_read");
+    int rc = WSPR_OK;
+    const int prev = fe->buffer_index ^ 1;
+    FCK(cudaSetDevice(fe->device));
+    FCK(cudaMemcpyAsync(I, fe->I[prev], (size_t)fe->nstreams * fe->cap * sizeof(float), cudaMemcpyDeviceToHost, fe->st));
+    FCK(cudaMemcpyAsync(Q, fe->Q[prev], (size_t)fe->nstreams * fe->cap * sizeof(float), cudaMemcpyDeviceToHost, fe->st));
+    FCK(cudaStreamSynchronize(fe->st));
+    rc = fe->iq_index[prev];
+done:
+    return rc;
+}
+
+extern "C" int wspr_frontend_samples(wspr_frontend *fe) { return fe ? fe->iq_index[fe->buffer_index] : WSPR_ERR_ARG; }

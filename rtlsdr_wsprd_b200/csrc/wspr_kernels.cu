@@ -30,7 +30,9 @@ __constant__ float c_floor_snr;
 __constant__ short c_mettab[2][256] = WSPR_METTAB_INIT;
 __device__ const double g_tw[256][2] = FFT512_TWIDDLE_INIT;
 
+void init_kernel_attributes();
 void upload_tables(const HostTables &t) {
+    init_kernel_attributes();
     cudaMemcpyToSymbol(c_window_g, t.window, sizeof t.window);
     cudaMemcpyToSymbol(c_lpf_w, t.lpf_w, sizeof t.lpf_w);
     cudaMemcpyToSymbol(c_lpf_psum, t.lpf_psum, sizeof t.lpf_psum);
@@ -827,8 +829,8 @@ __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, c
     Attempt *a = (i < njobs) ? &att0[job_list[i]] : nullptr;
     const bool want = a != nullptr && a->gate;
     FanoResult r;
-    fano_dense(r, want, want ? a->sym : nullptr, &c_mettab[0][0], delta, maxcycles, budget, FanoNoStop(),
-               FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
+    fano_dense<false>(r, want, want ? a->sym : nullptr, &c_mettab[0][0], delta, maxcycles, budget, FanoNoStop(),
+               FanoSmem::at(fano_smem, 512u));
     if (want) {
         a->ok = (r.rc == 0);
         a->unfinished = (r.rc == FANO_STOPPED);
@@ -953,8 +955,8 @@ __global__ void __launch_bounds__(32) k_chain_fano(Job *__restrict__ jobs, CapSt
     const bool want = mine && cs.gate[idt];
     FanoResult r;
     ChainStop stop{&cs.best, idt};
-    fano_dense(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
-               FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
+    fano_dense<false>(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
+               FanoSmem::at(fano_smem, 512u));
     if (mine) {
         cs.ok[idt] = want && (r.rc == 0);
         cs.unfinished[idt] = want && (r.rc == FANO_STOPPED);
@@ -1010,16 +1012,22 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
                                                   unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
                                                   unsigned long long *__restrict__ clocks, unsigned char *__restrict__ gmem) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
+    const bool fast = (solo & 4) != 0;
+    solo &= 3;
     const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * 32 + threadIdx.x);
     const bool want = i < n && (!solo || threadIdx.x == 0);
     FanoResult r;
     const long long t0 = clock64();
+    const unsigned char *sym = symbols + (size_t)(want ? i : 0) * NSYM;
     if (gmem)
-        fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                   FanoGmem{gmem + (size_t)blockIdx.x * FANO_WARP_SMEM_BYTES, 512u});
+        fano_dense<true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                         FanoGmem{gmem + (size_t)blockIdx.x * FANO_WARP_SMEM_BYTES, 512u});
+    else if (fast)                                             // the instantiation the decode kernels use
+        fano_dense<false>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                          FanoSmem::at(fano_smem, 512u));
     else
-        fano_dense(r, want, symbols + (size_t)(want ? i : 0) * NSYM, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                   FanoSmem{(unsigned)__cvta_generic_to_shared(fano_smem), 512u});
+        fano_dense<true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                         FanoSmem::at(fano_smem, 512u));
     if (!want) return;
     if (clocks) clocks[i] = (unsigned long long)(clock64() - t0);
     rc[i] = r.rc;
@@ -1029,21 +1037,13 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
     for (int k = 0; k < 12; k++) data[(size_t)i * 12 + k] = r.data[k];
 }
 size_t fano_warp_scratch_bytes() { return FANO_WARP_SMEM_BYTES; }
-static void fano_attrs() {                                    // opt in to > 48 KB of dynamic shared memory, once
-    static std::atomic<bool> done{false};
-    if (done.load()) return;
-    cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    done.store(true);
-}
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
                       unsigned char *gmem, cudaStream_t st) {
     if (n <= 0) return;
     fano_attrs();
     const int blocks = (solo & 1) ? n : (n + 31) / 32;
-    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 1, rc, metric,
+    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 5, rc, metric,
                                                                    cycles, maxnp, data, clocks, gmem);
     LAUNCHED();
 }
@@ -1196,17 +1196,19 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
     cprod[(size_t)s * CPAD + NFILT + ii] = c;
 }
 
-constexpr int LPF_THREADS = 256;
 constexpr int LPF_R = 4;                                     // consecutive outputs per thread
-constexpr int LPF_TILE = LPF_THREADS * LPF_R;                // 1024 outputs per CTA
-constexpr int LPF_SPAN = LPF_TILE + NFILT;                   // inputs per tile (1384, multiple of 4)
-constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
 
+// LPF_THREADS = 256: 1024 outputs per CTA.  (One-warp CTAs of 128 outputs were tried, to let a scheduler that also hosts a
+// long-running Fano warp simply take fewer of them: 3 % slower end to end -- 3.8x the staging traffic and 8x the CTAs.)
+template <int LPF_THREADS>
 __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, float *__restrict__ Q,
                                                          const CapState *__restrict__ caps, const int *__restrict__ sublist,
                                                          const Counters *cnt, const float2 *__restrict__ ref,
                                                          const float2 *__restrict__ cprod, int np, int stride, pk2 negzero,
                                                          pk2 one) {
+    constexpr int LPF_TILE = LPF_THREADS * LPF_R;            // outputs per CTA
+    constexpr int LPF_SPAN = LPF_TILE + NFILT;               // inputs per tile (multiple of 4)
+    constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
     __shared__ __align__(8) float2 sc[LPF_R * LPF_PITCH];
     const int s = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
     if (s >= cnt->nsub) return;
@@ -1274,8 +1276,8 @@ void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublis
     LAUNCHED();
     k_sub_ref<<<dim3(nsub_max, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
-    k_sub_lpf<<<dim3(nsub_max, (NSIG + LPF_TILE - 1) / LPF_TILE), LPF_THREADS, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod,
-                                                                                        p.np, p.stride, PK_NEGZERO, PK_ONE);
+    k_sub_lpf<256><<<dim3(nsub_max, (NSIG + 1023) / 1024), 256, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np, p.stride,
+                                                                         PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
 
@@ -1376,5 +1378,48 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
     k_sync_generic<<<dim3(nl, nf), 192, 0, st>>>(I, Q, np, freq, ifmin, fstep, lagmin, lagstep, drift, P, PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
+
+// Opt in to > 48 KB of dynamic shared memory, and ask for the LARGEST shared-memory carve-out for every kernel that shares
+// an SM with the long Fano runs.  An SM cannot change its L1/shared split while a CTA is resident: with the driver's
+// per-kernel default a one-warp Fano CTA (84 KB) pins its SM at the smallest split that holds it for the 100+ ms it runs,
+// and the bulk kernels (K4: 2 x 47 KB) then cannot be placed on that SM at all -- measured with tools/exp_interference.py:
+// one such CTA per SM serialises the whole decode behind it.  With one common split nothing ever has to wait for an SM to
+// drain.  (WSPR_CARVEOUT=default restores the driver's choice, for A/B measurements.)
+static void fano_attrs() {
+    static std::atomic<bool> done{false};
+    if (done.load()) return;
+    cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)
+    const char *e = getenv("WSPR_CARVEOUT");
+    const char mode = e ? e[0] : 'd';
+    int mx = cudaSharedmemCarveoutMaxShared;
+    const bool numeric = mode >= '0' && mode <= '9';
+    if (numeric) mx = atoi(e);
+    if (mode == 'c' || mode == 'm' || numeric) {
+        cudaFuncSetAttribute(k_fano_round, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_fano_test, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    }
+    if (mode == 'm' || numeric) {
+        cudaFuncSetAttribute(k_jitter_soft, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_spectrogram, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_coarse, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sync_lags, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_pick_lag, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_pick_freq, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sync_freqs, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sub_phase, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sub_ref, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sub_lpf<256>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_plan, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_collect, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    }
+    done.store(true);
+}
+void init_kernel_attributes() { fano_attrs(); }
 
 }  // namespace wspr

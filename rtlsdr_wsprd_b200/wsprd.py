@@ -54,7 +54,8 @@ def default_options(freq=144489000, npasses=2, subtraction=1, quickmode=0, useha
 
 
 def library_path():
-    return os.path.join(HERE, "libwsprd_b200.so")
+    """The in-tree build; WSPR_B200_LIB selects another build of the same library (A/B measurements)."""
+    return os.environ.get("WSPR_B200_LIB") or os.path.join(HERE, "libwsprd_b200.so")
 
 
 def build_library(force=False):
@@ -118,6 +119,16 @@ def library():
     lib.wspr_decimate_batch.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_int, C.c_int]
     lib.wspr_decimate_device.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.wspr_decimate_last_ms.restype = C.c_float
+    if hasattr(lib, "wspr_frontend_create"):                  # (absent from older builds selected through WSPR_B200_LIB)
+        lib.wspr_frontend_create.restype = vp
+        lib.wspr_frontend_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.wspr_frontend_destroy.restype = None
+        lib.wspr_frontend_destroy.argtypes = [vp]
+        lib.wspr_frontend_push.argtypes = [vp, vp, C.c_size_t, C.c_uint32]
+        lib.wspr_frontend_samples.argtypes = [vp]
+        lib.wspr_frontend_swap.argtypes = [vp]
+        lib.wspr_frontend_read.argtypes = [vp, vp, vp]
+        lib.wspr_frontend_slot_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip]
     lib.sync_and_demodulate.restype = None
     lib.sync_and_demodulate.argtypes = [fp, fp, C.c_long, up, fp, C.c_int, C.c_int, C.c_float, ip, C.c_int, C.c_int,
                                         C.c_int, fp, C.c_int, fp, C.c_int]
@@ -367,6 +378,67 @@ def decimate_device(raw_ptr, nstreams, n_iq, stream_stride_bytes, i_ptr, q_ptr, 
                                               int(q_ptr), int(out_stride), int(max_out), int(device)),
                "wspr_decimate_device", frontend=True)
     return n, float(library().wspr_decimate_last_ms())
+
+
+class FrontEnd:
+    """Streaming front end for `nstreams` receivers in lockstep: the state rtlsdr_callback keeps between calls
+    (rtlsdr_wsprd.c:126-244) plus the reference's double buffer (rtlsdr_wsprd.c:80-87,1181-1183).
+
+    push(chunk) per received buffer; at every slot boundary swap() then read() (or hand_off(decoder)) for the slot that
+    just ended -- what the daemon's main loop and decoder thread do."""
+
+    def __init__(self, nstreams=1, slot_samples=NSAMP, device=-1):
+        self.lib = library()
+        self.nstreams, self.slot_samples = int(nstreams), int(slot_samples)
+        self.fe = self.lib.wspr_frontend_create(int(device), self.nstreams, self.slot_samples)
+        if not self.fe:
+            raise WsprCudaError("wspr_frontend_create: %s" % (self.lib.wspr_frontend_last_error() or b"").decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "fe", None):
+            self.lib.wspr_frontend_destroy(self.fe)
+            self.fe = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def push(self, raw):
+        """raw: uint8[nstreams, nbytes] (or uint8[nbytes] for one stream), interleaved (I,Q); nbytes % 8 == 0."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        if raw.ndim == 1:
+            raw = raw[None, :]
+        assert raw.shape[0] == self.nstreams, (raw.shape, self.nstreams)
+        return _check(self.lib.wspr_frontend_push(self.fe, raw.ctypes.data, raw.shape[1], raw.shape[1]),
+                      "wspr_frontend_push", frontend=True)
+
+    def samples(self):
+        return int(self.lib.wspr_frontend_samples(self.fe))
+
+    def swap(self):
+        return _check(self.lib.wspr_frontend_swap(self.fe), "wspr_frontend_swap", frontend=True)
+
+    def read(self):
+        """(I, Q, n): the slot that ended at the last swap, float32[nstreams, slot_samples], zero beyond n."""
+        I = np.zeros((self.nstreams, self.slot_samples), np.float32)
+        Q = np.zeros((self.nstreams, self.slot_samples), np.float32)
+        n = _check(self.lib.wspr_frontend_read(self.fe, I.ctypes.data, Q.ctypes.data), "wspr_frontend_read", frontend=True)
+        return I, Q, n
+
+    def hand_off(self, decoder):
+        """Give the ended slot to a BatchDecoder without leaving the device, peak-normalised like decoder() does
+        (rtlsdr_wsprd.c:285-305).  Returns the samples the slot holds."""
+        di, dq, stride = C.c_void_p(), C.c_void_p(), C.c_int()
+        n = _check(self.lib.wspr_frontend_slot_device(self.fe, C.byref(di), C.byref(dq), C.byref(stride)),
+                   "wspr_frontend_slot_device", frontend=True)
+        assert decoder.samples <= stride.value
+        decoder.upload_device(di.value, dq.value, self.nstreams, stride.value)
+        decoder.normalise()
+        return n
 
 
 # ---- host-side formats either side of the path (SURVEY 8f N1/N2) --------------------------------------------------

@@ -337,6 +337,13 @@ def test_fano_kernel_against_oracle_random_vectors():
                 assert (got["rc"][k], got["metric"][k], got["cycles"][k], got["maxnp"][k]) == x[:4], (maxcycles, solo, k)
                 if x[0] == 0:
                     assert bytes(got["data"][k][:10]) == x[4]
+        # the instantiation the decode kernels run (time-out test every 256 trips, maxnp not tracked): return code, cycle
+        # count and decoded bytes as fano.c's; the path metric too whenever the decode succeeds
+        got = w.fano_batch(subset, maxcycles=maxcycles, solo=4)
+        for k, x in enumerate(want):
+            assert (got["rc"][k], got["cycles"][k]) == (x[0], x[2]), (maxcycles, "fast", k)
+            if x[0] == 0:
+                assert got["metric"][k] == x[1] and bytes(got["data"][k][:10]) == x[4]
     # a budgeted run either finishes with the same answer or reports FANO_STOPPED (2) -- never a different answer
     got = w.fano_batch(vecs, maxcycles=10000, stop_after=2048)
     full = w.fano_batch(vecs, maxcycles=10000)
@@ -400,3 +407,61 @@ def test_frontend_full_length_stream_then_decode():
     r, _, _ = po.decode(po.oracle(), a, b)
     assert H.results_equal(r, spots[0, : nres[0]])
     assert nres[0] >= 1 and spots[0, 0]["message"] == b"K1JT FN20 20"
+
+
+def test_streaming_frontend_matches_callback_across_pushes_and_slots():
+    """wspr_frontend_push / _swap (the daemon's receive callback and slot switch, rtlsdr_wsprd.c:126-244,1181-1183):
+    ragged chunk sizes, filter state carried across pushes and across slots, outputs beyond the slot length dropped."""
+    n_iq = 6401 * 150 + 2002                         # (2 * n_iq is a multiple of 8, like every chunk below)
+    rng = np.random.default_rng(99)
+    raw = rng.integers(0, 256, size=(3, 2 * n_iq), dtype=np.uint8)
+    raw[1, : 2 * 6401 * 40] = 0                      # rails: the int8 negation wrap on every negated sample
+    raw[2, 2 * 6401 * 20:] = 255
+    want = [oracle_decimate(raw[s], n_iq, 200) for s in range(3)]          # whole stream, zero initial state
+    assert want[0][2] == 150
+    chunks = [65536, 8, 12800, 16, 262144, 24, 65536 * 3, 12808, 40]
+    with w.FrontEnd(3, slot_samples=64) as fe:
+        pos, k, produced, slots = 0, 0, 0, []
+        while pos < 2 * n_iq:
+            nb = min(chunks[k % len(chunks)], 2 * n_iq - pos)
+            k += 1
+            produced += fe.push(raw[:, pos:pos + nb])
+            pos += nb
+            if len(slots) == 0 and produced >= 20:       # first slot switch, part-way through
+                slots.append((produced, fe.swap(), fe.read()))
+            elif len(slots) == 1 and produced >= 150:    # second slot overflowed its 64 samples
+                slots.append((produced, fe.swap(), fe.read()))
+        assert produced == 150 and fe.samples() == 0
+    (p0, n0, (I0, Q0, r0)), (p1, n1, (I1, Q1, r1)) = slots
+    assert n0 == r0 == min(p0, 64) and n1 == r1 == 64 and p1 - p0 > 64
+    for s in range(3):
+        io, qo, _ = want[s]
+        assert np.array_equal(I0[s, :n0], io[:n0]) and np.array_equal(Q0[s, :n0], qo[:n0])
+        assert not I0[s, n0:].any() and not Q0[s, n0:].any()
+        assert np.array_equal(I1[s], io[p0:p0 + 64]) and np.array_equal(Q1[s], qo[p0:p0 + 64])
+
+
+def test_streaming_frontend_against_reference_callback_and_decoder_hand_off():
+    """One receiver fed librtlsdr-sized buffers (65536 bytes, rtlsdr_wsprd.c:42): identical to the reference's own
+    rtlsdr_callback; then the device-resident hand-off into a decode context equals upload + normalise."""
+    try:
+        ref = po.RefFrontend()
+    except (FileNotFoundError, OSError):
+        pytest.skip("compiled reference front end not available")
+    n_bytes = 65536 * 60
+    raw = np.random.default_rng(5).integers(0, 256, size=n_bytes, dtype=np.uint8)
+    ref.push(raw)
+    ir, qr = ref.read()
+    with w.FrontEnd(1) as fe:
+        for off in range(0, n_bytes, 65536):
+            fe.push(raw[off:off + 65536])
+        n = fe.swap()
+        I, Q, _ = fe.read()
+        assert n == len(ir) == n_bytes // 2 // 6401
+        assert np.array_equal(I[0, :n], ir) and np.array_equal(Q[0, :n], qr)
+        with w.BatchDecoder(1) as d:
+            assert fe.hand_off(d) == n
+            _, _, Id, Qd = d.download(samples=True)
+    a, b = I[0].copy(), Q[0].copy()
+    po.oracle().oracle_normalise(a.ctypes.data_as(FP), b.ctypes.data_as(FP), a.shape[0])
+    assert np.array_equal(Id[0], a) and np.array_equal(Qd[0], b)
