@@ -39,8 +39,8 @@ BYTES_PER_CAPTURE = 360000 + 80 * 10 + 4
 SYNC_BYTES_PER_CANDIDATE = (162 * 256 + 256) * 8 + 33 * 162 * 16      # IQ window read + per-(lag,symbol) tone powers written
 SYNC_FLOP_PER_CANDIDATE = 33 * 162 * 256 * 32                         # 4 tones x (4 mul + 4 add) per sample, unfused
 # dram__bytes_read.sum + dram__bytes_write.sum of k_sync_lags per candidate, from the ncu --set full capture summarised in
-# profiles/r1_ncu_full_sync_lags_sub_lpf.txt (1024 candidates per launch: 344.65 MB read + 75.10 MB written)
-SYNC_DRAM_BYTES_PER_CANDIDATE = (344.651e6 + 75.099e6) / 1024
+# profiles/r1_ncu_full_packed.txt (1024 candidates per launch: 343.33 MB read + 70.86 MB written)
+SYNC_DRAM_BYTES_PER_CANDIDATE = (343.327e6 + 70.856e6) / 1024
 
 
 # ---- corpus (host, seeded; identical arrays go to the GPU path and to the CPU reference) --------------------------
@@ -255,7 +255,7 @@ def run_ours(args):
         roofline = {"kernel": "k_sync_lags (sync_and_demodulate mode 0)", "bound": "hbm", "achieved": round(gbs, 2), "peak": hbm_peak,
                     "unit": "GB/s", "frac": round(gbs / hbm_peak, 5),
                     "traffic": int(candidates / max(sync_launches, 1) * SYNC_DRAM_BYTES_PER_CANDIDATE),
-                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_sync_lags_sub_lpf.txt, scaled to the mean candidates per launch",
+                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_packed.txt, scaled to the mean candidates per launch",
                     "peak_source": peak_src,
                     "launches": sync_launches, "avg_launch_ms": round(sync_ms / max(sync_launches, 1), 4),
                     "note": "FP32-issue bound, not HBM bound: %.2f TFLOP/s unfused fp32 (%.3g flop per candidate)"
@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--captures", type=int, default=CAPTURES_PER_GPU, help="captures per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=96, help="captures decoded by the CPU baseline / parity leg")
     ap.add_argument("--no-frontend", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight per GPU (contexts driven by host threads)")
+    ap.add_argument("--depth", type=int, default=9, help="batches in flight per GPU (contexts driven by host threads)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -90,7 +90,7 @@ struct wspr_ctx {
     Job *jobs = nullptr;           // [maxcap] the candidate each capture is working on
     Attempt *att0 = nullptr;       // [maxcap] its jitter-0 attempt
     int *ident = nullptr, *setup_list = nullptr, *job_list = nullptr, *res_list = nullptr, *sub_list = nullptr;
-    float4 *P0 = nullptr, *P1 = nullptr;
+    float4 *P0 = nullptr, *P1 = nullptr, *tabs = nullptr;
     float *phi0 = nullptr;
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
@@ -115,7 +115,7 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
-                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->phi0, c->ref, c->cprod, c->cnt, c->stats, c->preload};
+                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->tabs, c->phi0, c->ref, c->cprod, c->cnt, c->stats, c->preload};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (SideSlot &s : c->side) {
@@ -173,7 +173,8 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(dalloc(&c->sub_list, B));
     CK(dalloc(&c->P0, B * MAXLAGS * NSYM));
     CK(dalloc(&c->P1, B * NFREQ1 * NSYM));
-    CK(dalloc(&c->phi0, B * NSYM));
+    CK(dalloc(&c->tabs, B * NFREQ1 * 2 * SPS));
+    CK(dalloc(&c->phi0, B * (NSIG / 32)));                 // running phase of every 32nd sample of a subtraction
     CK(dalloc(&c->ref, B * NSIG));
     CK(dalloc(&c->cprod, B * CPAD));
     CK(dalloc(&c->cnt, 1));
@@ -431,13 +432,13 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 }
                 CK(cudaEventRecord(c->kev[kev_used], c->st));
             }
-            launch_sync_lags(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, p, c->st);
+            launch_sync_lags(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->tabs, p, c->st);
             if (c->time_kernels) {
                 CK(cudaEventRecord(c->kev[kev_used + 1], c->st));
                 kev_used += 2;
                 c->kev_jobs.push_back(h.njobs);
             }
-            launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->P1, c->att0, p, c->st);
+            launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->P1, c->tabs, c->att0, p, c->st);
             launch_fano_round(c->att0, c->job_list, h.njobs, p, c->st);
             launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, side->list, side->count, c->cnt, p,
                            c->st);
@@ -657,11 +658,28 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     return ret;
 }
 
-// Experiment hook (tools/exp_interference.py): put `nctas` one-warp Fano CTAs of hopeless attempts (the shape of k_chain_fano)
-// in flight on a private stream and return at once; wspr_debug_fano_load(0, 0) waits for them.  Not part of the product path.
-extern "C" int wspr_debug_fano_load(int nctas, unsigned maxcycles) {
+// Experiment hook (tools/exp_interference.py): put `nctas` one-warp CTAs in flight on a private stream and return at once;
+// wspr_debug_fano_load(0, 0, 0) waits for them.  mode 0: Fano on hopeless attempts, tree state in shared memory (the shape of
+// k_chain_fano); 2: the same with the tree state in global memory (no shared memory held); 8: CTAs that hold 84 KB of
+// shared memory and sleep; 9: sleep without shared memory; 10: a dependent integer loop at ~1 instruction per 4 clocks
+// without shared memory.  Not part of the product path.
+__global__ void k_debug_resident(int mode, long long clocks, unsigned *sink) {
+    extern __shared__ unsigned dbg_smem[];
+    const long long t0 = clock64();
+    unsigned x = threadIdx.x;
+    if (mode == 10) {
+        while (clock64() - t0 < clocks) {
+#pragma unroll
+            for (int k = 0; k < 64; k++) x = x * 1664525u + 1013904223u;
+        }
+    } else {
+        while (clock64() - t0 < clocks) __nanosleep(2000);
+    }
+    if (x == 0xdeadbeefu) sink[0] = x + (mode == 8 ? dbg_smem[threadIdx.x] : 0u);
+}
+extern "C" int wspr_debug_fano_load(int nctas, unsigned maxcycles, int mode) {
     static cudaStream_t st = nullptr;
-    static unsigned char *d_sym = nullptr;
+    static unsigned char *d_sym = nullptr, *d_g = nullptr;
     static int *d_i = nullptr;
     static unsigned *d_u = nullptr;
     static unsigned char *d_data = nullptr;
@@ -672,17 +690,25 @@ extern "C" int wspr_debug_fano_load(int nctas, unsigned maxcycles) {
         CK(cudaMalloc((void **)&d_i, (size_t)cap * sizeof(int)));
         CK(cudaMalloc((void **)&d_u, (size_t)3 * cap * sizeof(unsigned)));
         CK(cudaMalloc((void **)&d_data, (size_t)cap * 12));
+        CK(cudaMalloc((void **)&d_g, (size_t)1024 * fano_warp_scratch_bytes()));
         std::vector<unsigned char> h((size_t)cap * NSYM);
         unsigned x = 12345u;
         for (auto &b : h) { x = x * 1664525u + 1013904223u; b = (unsigned char)(x >> 24); }
         CK(cudaMemcpy(d_sym, h.data(), h.size(), cudaMemcpyHostToDevice));
+        CK(cudaFuncSetAttribute(k_debug_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, 84480));
     }
     if (nctas <= 0) {
         CK(cudaStreamSynchronize(st));
         return WSPR_OK;
     }
-    const int n = std::min(nctas * 32, cap);
-    launch_fano_test(d_sym, n, 60, maxcycles, 0, 0, d_i, d_u, d_u + cap, d_u + 2 * cap, d_data, nullptr, nullptr, st);
+    nctas = std::min(nctas, 1024);
+    if (mode >= 8) {
+        // maxcycles x 81 Fano cycles at ~290 clocks each, so that the load lasts as long as the Fano loads do
+        k_debug_resident<<<nctas, 32, mode == 8 ? 84480 : 0, st>>>(mode, (long long)maxcycles * 81 * 290, d_u);
+    } else {
+        launch_fano_test(d_sym, nctas * 32, 60, maxcycles, 0, mode & 2, d_i, d_u, d_u + cap, d_u + 2 * cap, d_data, nullptr,
+                         (mode & 2) ? d_g : nullptr, st);
+    }
     CK(cudaGetLastError());
     return WSPR_OK;
 }

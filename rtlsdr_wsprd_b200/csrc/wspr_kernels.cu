@@ -474,7 +474,11 @@ __device__ __forceinline__ float4 acc_power(const Acc8 &a) {   // :211-214  (dou
 // Shared phasor tables for the packed form: tabp[j] = {c0,c1,s0,s1}, tabp[256+j] = {c2,c3,s2,s3}; a thread keeps the
 // sums of tones (0,1) and (2,3) side by side: AI01 += (x,x)*(c0,c1); AI01 += (y,y)*(s0,s1); AQ01 += (-x,-x)*(s0,s1);
 // AQ01 += (y,y)*(c0,c1) -- per tone exactly the reference's (i + x*c) + y*s and (q - x*s) + y*c.
-constexpr int SYMS_PER_CTA = 18;                           // 162 = 9 x 18
+#ifndef WSPR_K4_SYMS
+#define WSPR_K4_SYMS 18                                    // (build-time knobs for A/B measurements of the CTA shape)
+#define WSPR_K4_MINB 2
+#endif
+constexpr int SYMS_PER_CTA = WSPR_K4_SYMS;                 // 162 = 9 x 18
 constexpr int LAG_WIN = SYMS_PER_CTA * SPS + SPS;          // 4864 samples cover every lag of the group
 constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 609
 constexpr int LAG_THREADS = (MAXLAGS * SYMS_PER_CTA + 31) / 32 * 32;   // 608
@@ -498,10 +502,44 @@ __device__ __forceinline__ void build_tables(float fp, float4 *tab, int t) {
     }
 }
 
-__global__ void __launch_bounds__(LAG_THREADS, 2) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
+// The shared tables of the drift == 0 case, built once per (job, hypothesis) in global memory -- one thread per tone runs
+// the 256-step recurrence -- instead of once per CTA behind a barrier (K4 has nine CTAs per job, k_sync_freqs one CTA per
+// hypothesis whose main loop is hardly longer than the recurrence).  side = 0: the job's own frequency, slot 2 (K4);
+// side = 1: the mode-1 hypotheses freq + (fi - 2) * 0.1 (:151), slots 0..4, after k_pick_lag has settled freq.
+__global__ void k_tables(const Job *__restrict__ jobs, const int *__restrict__ job_list, int njobs, float4 *__restrict__ tabs,
+                         int side) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tone = tid & 3, q = tid >> 2, nh = side ? NFREQ1 : 1;
+    const int jx = q / nh, fi = side ? q - jx * nh : 2;
+    if (jx >= njobs) return;
+    const Job &job = jobs[job_list[jx]];
+    if (job.drift != 0.0f) return;                             // per-symbol frequencies: phasors advance in registers
+    if (side && fi == 2 && job.lbest >= 0) return;             // that row is copied from the lag search, no table needed
+    const float fstep = 0.1f;
+    const float f0 = side ? job.freq + (float)(fi - 2) * fstep : job.freq;
+    float cd[4], sd[4];
+    tone_seeds(f0, cd, sd);
+    const float cdt = cd[tone], sdt = sd[tone];
+    float *base = reinterpret_cast<float *>(tabs + ((size_t)jx * NFREQ1 + fi) * (2 * SPS)) + (tone >> 1) * (SPS * 4) + (tone & 1);
+    float c = 1.0f, s = 0.0f;
+    for (int j = 0; j < SPS; j++) {
+        base[j * 4] = c;
+        base[j * 4 + 2] = s;
+        float cn = c * cdt - s * sdt;
+        float sn = c * sdt + s * cdt;
+        c = cn;
+        s = sn;
+    }
+}
+__device__ __forceinline__ void load_tables(float4 *tab, const float4 *__restrict__ tabs, int slot, int fi, int t, int nthreads) {
+    const float4 *g = tabs + ((size_t)slot * NFREQ1 + fi) * (2 * SPS);
+    for (int m = t; m < 2 * SPS; m += nthreads) tab[m] = g[m];
+}
+
+__global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
                                                               const Job *__restrict__ jobs, const int *__restrict__ job_list,
-                                                              float4 *__restrict__ P0, int np, int stride, int lagstep,
-                                                              int nlags, pk2 negzero, pk2 one) {
+                                                              float4 *__restrict__ P0, const float4 *__restrict__ tabs, int np,
+                                                              int stride, int lagstep, int nlags, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float2 win[8 * LAG_PITCH];
     const Job &job = jobs[job_list[blockIdx.x]];
@@ -518,7 +556,7 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) k_sync_lags(const float *__res
         if (k > 0 && k < np) v = make_float2(ip[k], qp[k]);  // k > 0: the reference never reads sample 0 (:199)
         win[(m & 7) * LAG_PITCH + (m >> 3)] = v;
     }
-    if (shared_tab) build_tables(f0, tab, t);
+    if (shared_tab) load_tables(tab, tabs, blockIdx.x, 2, t, LAG_THREADS);
     __syncthreads();
 
     const int sym_local = t / nlags, lagidx = t - sym_local * nlags;
@@ -610,10 +648,12 @@ __global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const i
     }
 }
 
-void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0,
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0, float4 *tabs,
                       const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, job_list, P0, p.np, p.stride,
+    k_tables<<<(njobs * 4 + 127) / 128, 128, 0, st>>>(jobs, job_list, njobs, tabs, 0);
+    LAUNCHED();
+    k_sync_lags<<<dim3(njobs, NSYM / SYMS_PER_CTA), LAG_THREADS, 0, st>>>(I, Q, jobs, job_list, P0, tabs, p.np, p.stride,
                                                                           p.lagstep, p.nlags, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_lag<<<njobs, 64, 0, st>>>(jobs, job_list, P0, p.lagstep, p.nlags);
@@ -680,8 +720,8 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
 // mode 1: five frequencies at the best lag (:722-726)
 __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I, const float *__restrict__ Q,
                                                     const Job *__restrict__ jobs, const int *__restrict__ job_list,
-                                                    const float4 *__restrict__ P0, float4 *__restrict__ P1, int np,
-                                                    int stride, pk2 negzero, pk2 one) {
+                                                    const float4 *__restrict__ P0, float4 *__restrict__ P1,
+                                                    const float4 *__restrict__ tabs, int np, int stride, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     const Job &job = jobs[job_list[blockIdx.x]];
     const int fi = blockIdx.y, t = threadIdx.x;
@@ -693,7 +733,7 @@ __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I,
     const float fstep = 0.1f;
     const float f0 = job.freq + (float)(fi - 2) * fstep;      // :151
     const bool shared_tab = (job.drift == 0.0f);
-    if (shared_tab) build_tables(f0, tab, t);
+    if (shared_tab) load_tables(tab, tabs, blockIdx.x, fi, t, 192);
     __syncthreads();
     if (t >= NSYM) return;
     const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
@@ -800,9 +840,11 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_
 }
 
 void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, const float4 *P0, float4 *P1,
-                       Attempt *att0, const DecodeParams &p, cudaStream_t st) {
+                       float4 *tabs, Attempt *att0, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, p.np, p.stride, PK_NEGZERO, PK_ONE);
+    k_tables<<<(njobs * NFREQ1 * 4 + 127) / 128, 128, 0, st>>>(jobs, job_list, njobs, tabs, 1);
+    LAUNCHED();
+    k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
     LAUNCHED();
@@ -933,21 +975,29 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
     }
 }
 
-// One-warp CTAs.  CTA e < n runs attempts 0..31 of candidate e; CTA n + j runs the remaining attempts 32..42 of candidates
-// 2j (lanes 0..10) and 2j+1 (lanes 16..26).  What a parked candidate holds on an SM is therefore 1.5 small pieces of
-// shared memory instead of one 170 KB block that would crowd the bulk kernels out of that SM for the 100+ ms a hopeless
-// candidate takes.  The piece that finishes last picks the winner and hands the capture back.
-__global__ void __launch_bounds__(32) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
-                                                   const int *__restrict__ defer_list, ChainScratch *__restrict__ scratch, int n,
-                                                   int nattempts, int delta, unsigned maxcycles, int *__restrict__ stats) {
-    extern __shared__ __align__(16) unsigned char fano_smem[];
-    const int lane = threadIdx.x;
+// One-warp pieces.  Piece e < n runs attempts 0..31 of candidate e; piece n + j runs the remaining attempts 32..42 of
+// candidates 2j (lanes 0..10) and 2j+1 (lanes 16..26).  The piece that finishes last picks the winner and hands the capture
+// back.  A CTA carries CHAIN_PIECES pieces, one warp each, completely independent of each other (no CTA barrier).
+// One piece per CTA by default.  Two were tried (WSPR_CHAIN_PIECES=2), on the theory that what a resident Fano warp costs
+// the bulk kernels is per SM rather than per warp, so parked work should sit on half as many SMs: 9 % slower end to end
+// -- a 170 KB CTA has to wait for a nearly empty SM and then excludes everything else from it.
+constexpr int CHAIN_PIECES = 2;
+__global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
+                                                                 const int *__restrict__ defer_list,
+                                                                 ChainScratch *__restrict__ scratch, int n, int npieces,
+                                                                 int nattempts, int delta, unsigned maxcycles,
+                                                                 int *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char fano_smem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int piece = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
+    if (piece >= npieces) return;
+    unsigned char *fano_smem = fano_smem_all + (size_t)warp * FANO_WARP_SMEM_BYTES;
     int e, idt;
-    if ((int)blockIdx.x < n) {
-        e = blockIdx.x;
+    if (piece < n) {
+        e = piece;
         idt = lane;
     } else {
-        e = 2 * ((int)blockIdx.x - n) + (lane >> 4);
+        e = 2 * (piece - n) + (lane >> 4);
         idt = 32 + (lane & 15);
     }
     const bool mine = e < n && idt < nattempts;
@@ -964,7 +1014,7 @@ __global__ void __launch_bounds__(32) k_chain_fano(Job *__restrict__ jobs, CapSt
         for (int k = 0; k < 12; k++) cs.dec[idt][k] = r.data[k];
     }
     __syncwarp();
-    if (e < n && (lane & 15) == 0 && ((int)blockIdx.x >= n || lane == 0)) {   // one arrival per (piece, candidate)
+    if (e < n && (lane & 15) == 0 && (piece >= n || lane == 0)) {   // one arrival per (piece, candidate)
         const int pieces = nattempts > 32 ? 2 : 1;
         __threadfence();
         const int arrived = atomicAdd(&cs.done, 1);
@@ -1000,8 +1050,10 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, C
     const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
     // WSPR_DEBUG_CHAIN_MAXCYCLES: experiment knob (wrong results!) to measure what the long Fano runs cost
     static const unsigned dbg_maxcycles = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
-    k_chain_fano<<<nctas, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, defer_list, scratch, n, nattempts, p.delta,
-                                                         dbg_maxcycles ? dbg_maxcycles : p.maxcycles, stats);
+    // WSPR_CHAIN_PIECES: experiment knob (2 = two pieces per CTA)
+    static const int ppc = [] { const char *e = getenv("WSPR_CHAIN_PIECES"); int v = e ? atoi(e) : 1; return v >= 1 && v <= CHAIN_PIECES ? v : 1; }();
+    k_chain_fano<<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
+        jobs, caps, defer_list, scratch, n, nctas, nattempts, p.delta, dbg_maxcycles ? dbg_maxcycles : p.maxcycles, stats);
     LAUNCHED();
 }
 
@@ -1131,8 +1183,9 @@ void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list,
 // =========================================================================================================
 // K6  subtract_signal2 (wsprd.c:316-413)
 //   (a) the reference phase is a float running sum over all 41 472 samples; one thread per job replays the
-//       additions and records the phase at every symbol start;
-//   (b) per symbol: replay 256 additions, cos/sin (glibc-faithful), s(t)*conj(r(t)) into a zero-padded buffer;
+//       additions and records the phase every 32 samples;
+//   (b) per sample: at most 31 more additions from the recorded phase of its segment, cos/sin (glibc-faithful),
+//       s(t)*conj(r(t)) into a zero-padded buffer;
 //   (c) 360-tap low-pass (each output a sequential 360-term sum, four consecutive outputs per thread with a
 //       sliding register window), edge renormalisation, subtraction in place.
 // =========================================================================================================
@@ -1143,24 +1196,28 @@ __device__ __forceinline__ float sub_dphi(float f0, float drift, int i, unsigned
                                 ((double)cs - 1.5) * 375.0 / 256.0));
 }
 
+constexpr int PHI_SEG = 32;                                  // the running phase is recorded every PHI_SEG samples
 __global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__restrict__ sublist, const Counters *cnt,
-                            float *__restrict__ phi0) {
+                            float *__restrict__ phi_seg) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cnt->nsub) return;
     const CapState &cs = caps[sublist[s]];
+    float *out = phi_seg + (size_t)s * (NSIG / PHI_SEG);
     float phi = 0.0f;
     for (int i = 0; i < NSYM; i++) {
-        phi0[(size_t)s * NSYM + i] = phi;
-        float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
-        for (int j = 0; j < SPS; j++) phi = phi + dphi;
+        const float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
+        for (int j8 = 0; j8 < SPS / PHI_SEG; j8++) {
+            out[i * (SPS / PHI_SEG) + j8] = phi;
+#pragma unroll
+            for (int j = 0; j < PHI_SEG; j++) phi = phi + dphi;
+        }
     }
 }
 
 __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, const float *__restrict__ Q,
                                                  const CapState *__restrict__ caps, const int *__restrict__ sublist,
-                                                 const Counters *cnt, const float *__restrict__ phi0,
+                                                 const Counters *cnt, const float *__restrict__ phi_seg,
                                                  float2 *__restrict__ ref, float2 *__restrict__ cprod, int np, int stride) {
-    __shared__ float s_phi[SPS];
     const int s = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
     if (s >= cnt->nsub) return;
     const int cap = sublist[s];
@@ -1173,19 +1230,13 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
         if (z < tailn) c[NFILT + NSIG + z] = make_float2(0.0f, 0.0f);
         return;
     }
-    if (j == 0) {
-        float phi = phi0[(size_t)s * NSYM + i];
-        float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
-        for (int q = 0; q < SPS; q++) {
-            s_phi[q] = phi;
-            phi = phi + dphi;
-        }
-    }
-    __syncthreads();
-    const float phi = s_phi[j];
+    const int ii = i * SPS + j, k = cs.sub_shift + ii;
+    // the phase of sample ii: the recorded phase of its 32-sample segment, then the reference's additions up to ii
+    float phi = phi_seg[(size_t)s * (NSIG / PHI_SEG) + ii / PHI_SEG];
+    const float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
+    for (int q = 0; q < (j & (PHI_SEG - 1)); q++) phi = phi + dphi;
     float rc, rs;
     glibc_sincosf(phi, &rs, &rc);
-    const int ii = i * SPS + j, k = cs.sub_shift + ii;
     float2 c = make_float2(0.0f, 0.0f);
     if (k > 0 && k < np) {               // :375-381
         float x = I[(size_t)cap * stride + k], y = Q[(size_t)cap * stride + k];
@@ -1197,6 +1248,9 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
 }
 
 constexpr int LPF_R = 4;                                     // consecutive outputs per thread
+#ifndef WSPR_LPF_THREADS
+#define WSPR_LPF_THREADS 256                                 // (build-time knob for A/B measurements of the CTA shape)
+#endif
 
 // LPF_THREADS = 256: 1024 outputs per CTA.  (One-warp CTAs of 128 outputs were tried, to let a scheduler that also hosts a
 // long-running Fano warp simply take fewer of them: 3 % slower end to end -- 3.8x the staging traffic and 8x the CTAs.)
@@ -1276,8 +1330,9 @@ void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublis
     LAUNCHED();
     k_sub_ref<<<dim3(nsub_max, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
-    k_sub_lpf<256><<<dim3(nsub_max, (NSIG + 1023) / 1024), 256, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np, p.stride,
-                                                                         PK_NEGZERO, PK_ONE);
+    constexpr int T = WSPR_LPF_THREADS;
+    k_sub_lpf<T><<<dim3(nsub_max, (NSIG + 4 * T - 1) / (4 * T)), T, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np, p.stride,
+                                                                             PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
 
@@ -1390,7 +1445,7 @@ static void fano_attrs() {
     if (done.load()) return;
     cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
     // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)
     const char *e = getenv("WSPR_CARVEOUT");
     const char mode = e ? e[0] : 'd';
@@ -1413,7 +1468,7 @@ static void fano_attrs() {
         cudaFuncSetAttribute(k_sync_freqs, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_sub_phase, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_sub_ref, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sub_lpf<256>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_sub_lpf<WSPR_LPF_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_plan, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_collect, cudaFuncAttributePreferredSharedMemoryCarveout, mx);

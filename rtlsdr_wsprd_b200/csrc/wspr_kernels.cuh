@@ -148,10 +148,11 @@ void launch_candidates(const float *psT, Cand *cands, CapState *caps, float *sms
                        const DecodeParams &p, cudaStream_t st);
 void launch_coarse(const float *psT, Cand *cands, const CapState *caps, const int *list, int n, const DecodeParams &p,
                    cudaStream_t st);
-void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0,
+// tabs: [njobs][NFREQ1][2 * SPS] float4 scratch for the shared phasor tables (slot 2 = the job's own frequency)
+void launch_sync_lags(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, float4 *P0, float4 *tabs,
                       const DecodeParams &p, cudaStream_t st);
 void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job_list, int njobs, const float4 *P0, float4 *P1,
-                       Attempt *att0, const DecodeParams &p, cudaStream_t st);
+                       float4 *tabs, Attempt *att0, const DecodeParams &p, cudaStream_t st);
 // jitter-0 Fano attempts of the round (budgeted) and their triage into the resolve list / the deferred list
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st);
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
