@@ -41,6 +41,9 @@ SYNC_FLOP_PER_CANDIDATE = 33 * 162 * 256 * 32                         # 4 tones 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_sync_lags per candidate, from the ncu --set full capture summarised in
 # profiles/r1_ncu_full_packed.txt (1024 candidates per launch: 343.33 MB read + 70.86 MB written)
 SYNC_DRAM_BYTES_PER_CANDIDATE = (343.327e6 + 70.856e6) / 1024
+# the same for the front end (k_block_moments + k_comb_fir) per raw stream, profiles/r1_ncu_full_frontend.txt (4 streams per
+# launch: 2303.97 MB + 2.90 MB read, 5.64 MB written): the 576 MB of a stream are read exactly once
+FRONTEND_DRAM_BYTES_PER_STREAM = (2303.973e6 + 2.895e6 + 5.645e6) / 4
 
 
 # ---- corpus (host, seeded; identical arrays go to the GPU path and to the CPU reference) --------------------------
@@ -165,6 +168,10 @@ def run_ours(args):
     ncap = args.captures
     lo = rank * ncap                                   # weak scaling: every GPU gets its own contiguous shard of the corpus
     host_workers = max(1, (os.cpu_count() or 8) // world)
+    # every context is driven by a host thread that polls (yielding) for the two counter reads of a round; with fewer host
+    # cores per rank than contexts the threads sleep in the driver instead (read once, when the library loads)
+    if host_workers < args.depth:
+        os.environ.setdefault("WSPR_WAIT", "block")
 
     # pinned host planes (the e2e leg copies from these every step)
     hI = torch.empty((ncap, NSAMP), dtype=torch.float32).pin_memory()
@@ -277,7 +284,9 @@ def run_ours(args):
         ms = min(times[1:])
         gbs = nstreams * (2 * n_iq + 2 * 4 * 44992) / (ms * 1e-3) / 1e9
         frontend = {"kernel": "k_block_moments+k_comb_fir (rtlsdr_callback)", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "streams_per_s": round(nstreams / (ms * 1e-3), 1),
+                    "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "traffic": int(nstreams * FRONTEND_DRAM_BYTES_PER_STREAM),
+                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_frontend.txt, scaled to the streams per launch",
+                    "streams_per_s": round(nstreams / (ms * 1e-3), 1),
                     "workload": "%d raw streams x 288e6 u8 IQ pairs resident in HBM" % nstreams}
         del raw
 

@@ -174,7 +174,7 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(dalloc(&c->P0, B * MAXLAGS * NSYM));
     CK(dalloc(&c->P1, B * NFREQ1 * NSYM));
     CK(dalloc(&c->tabs, B * NFREQ1 * 2 * SPS));
-    CK(dalloc(&c->phi0, B * (NSIG / 32)));                 // running phase of every 32nd sample of a subtraction
+    CK(dalloc(&c->phi0, B * (NSIG / PHI_SEG)));            // running phase of every PHI_SEG-th sample of a subtraction
     CK(dalloc(&c->ref, B * NSIG));
     CK(dalloc(&c->cprod, B * CPAD));
     CK(dalloc(&c->cnt, 1));

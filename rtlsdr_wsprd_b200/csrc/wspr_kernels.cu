@@ -1183,8 +1183,8 @@ void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list,
 // =========================================================================================================
 // K6  subtract_signal2 (wsprd.c:316-413)
 //   (a) the reference phase is a float running sum over all 41 472 samples; one thread per job replays the
-//       additions and records the phase every 32 samples;
-//   (b) per sample: at most 31 more additions from the recorded phase of its segment, cos/sin (glibc-faithful),
+//       additions and records the phase every PHI_SEG samples;
+//   (b) per sample: at most PHI_SEG - 1 more additions from the recorded phase of its segment, cos/sin (glibc-faithful),
 //       s(t)*conj(r(t)) into a zero-padded buffer;
 //   (c) 360-tap low-pass (each output a sequential 360-term sum, four consecutive outputs per thread with a
 //       sliding register window), edge renormalisation, subtraction in place.
@@ -1196,7 +1196,6 @@ __device__ __forceinline__ float sub_dphi(float f0, float drift, int i, unsigned
                                 ((double)cs - 1.5) * 375.0 / 256.0));
 }
 
-constexpr int PHI_SEG = 32;                                  // the running phase is recorded every PHI_SEG samples
 __global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__restrict__ sublist, const Counters *cnt,
                             float *__restrict__ phi_seg) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1231,7 +1230,7 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
         return;
     }
     const int ii = i * SPS + j, k = cs.sub_shift + ii;
-    // the phase of sample ii: the recorded phase of its 32-sample segment, then the reference's additions up to ii
+    // the phase of sample ii: the recorded phase of its segment, then the reference's additions up to ii
     float phi = phi_seg[(size_t)s * (NSIG / PHI_SEG) + ii / PHI_SEG];
     const float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
     for (int q = 0; q < (j & (PHI_SEG - 1)); q++) phi = phi + dphi;
