@@ -1233,7 +1233,12 @@ __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, co
     // the phase of sample ii: the recorded phase of its segment, then the reference's additions up to ii
     float phi = phi_seg[(size_t)s * (NSIG / PHI_SEG) + ii / PHI_SEG];
     const float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
-    for (int q = 0; q < (j & (PHI_SEG - 1)); q++) phi = phi + dphi;
+    const int rem = j & (PHI_SEG - 1);
+#pragma unroll
+    for (int q = 0; q < PHI_SEG - 1; q++) {                  // (uniform instruction stream: lanes differ only in rem)
+        const float nxt = phi + dphi;
+        phi = (q < rem) ? nxt : phi;
+    }
     float rc, rs;
     glibc_sincosf(phi, &rs, &rc);
     float2 c = make_float2(0.0f, 0.0f);

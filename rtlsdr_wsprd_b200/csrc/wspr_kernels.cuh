@@ -19,7 +19,7 @@ constexpr int NJIT = 43;         // jitter attempts 0..42, wsprd.c:741
 constexpr int NFILT = 360;       // subtract_signal2 low-pass length, wsprd.c:325
 constexpr int NSIG = NSYM * SPS; // 41472 samples of one transmission
 constexpr int CPAD = 42240;      // padded length of the s*conj(r) product (NSIG + 2*NFILT, rounded up)
-constexpr int PHI_SEG = 32;     // subtract_signal2: the running phase is recorded every PHI_SEG samples (divides SPS)
+constexpr int PHI_SEG = 8;      // subtract_signal2: the running phase is recorded every PHI_SEG samples (divides SPS)
 constexpr int HASH_CAP = 224;    // per-capture callsign-hash entries kept on the device
 
 // struct cand, wsprd/wsprd.h:54-60
