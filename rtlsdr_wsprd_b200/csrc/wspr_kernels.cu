@@ -20,6 +20,7 @@ static std::atomic<unsigned long long> g_launches{0};   // contexts may be drive
 extern unsigned long long g_frontend_launches;   // wspr_frontend.cu
 unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend_launches; }
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+static void fano_attrs();                                  // one-time kernel attributes (end of this file)
 
 // ---- constant tables ----------------------------------------------------------------------------------
 __device__ float c_window_g[NFFT];    // (indexed in bit-reversed order by the lanes: global/L1, not the constant bank)
@@ -730,15 +731,95 @@ __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I,
             P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = P0[((size_t)blockIdx.x * MAXLAGS + job.lbest) * NSYM + t];
         return;
     }
+    const bool shared_tab = (job.drift == 0.0f);
+    if (shared_tab && fi != 2) return;                        // the side hypotheses of drift-free jobs: k_sync_freqs_shared
     const float fstep = 0.1f;
     const float f0 = job.freq + (float)(fi - 2) * fstep;      // :151
-    const bool shared_tab = (job.drift == 0.0f);
     if (shared_tab) load_tables(tab, tabs, blockIdx.x, fi, t, 192);
     __syncthreads();
     if (t >= NSYM) return;
     const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
     float fp = shared_tab ? f0 : symbol_freq(f0, job.drift, t);
     P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = correlate_symbol(ip, qp, np, job.shift + t * SPS, shared_tab, tab, fp, negzero, one);
+}
+
+// mode 1, drift == 0 (95 % of the candidates): the four side hypotheses of a job in ONE CTA, so that the 162 symbol windows
+// are read from global memory once (in 8-sample chunks, coalesced, double-buffered in shared memory) instead of once per
+// hypothesis with a 1 KB stride between lanes -- the per-hypothesis kernel above is bound by L2 traffic, not by arithmetic.
+// Thread (g, s) owns hypothesis g and symbol s; the sums are the reference's, sample by sample in order.
+constexpr int SF_CHUNK = 8;
+constexpr int SF_PITCH = SF_CHUNK + 1;
+constexpr int SF_GROUP = 192;                                  // threads per hypothesis (162 used)
+constexpr int SF_THREADS = 4 * SF_GROUP;
+constexpr int SF_SMEM_BYTES = 4 * 2 * SPS * 16 + 2 * NSYM * SF_PITCH * 8;
+__global__ void __launch_bounds__(SF_THREADS) k_sync_freqs_shared(const float *__restrict__ I, const float *__restrict__ Q,
+                                                                  const Job *__restrict__ jobs, const int *__restrict__ job_list,
+                                                                  float4 *__restrict__ P1, const float4 *__restrict__ tabs, int np,
+                                                                  int stride, pk2 negzero, pk2 one) {
+    extern __shared__ __align__(16) unsigned char sf_smem[];
+    float4 *tab = reinterpret_cast<float4 *>(sf_smem);                              // [4][2 * SPS]
+    float2 *buf = reinterpret_cast<float2 *>(sf_smem + 4 * 2 * SPS * 16);           // [2][NSYM][SF_PITCH]
+    const Job &job = jobs[job_list[blockIdx.x]];
+    if (job.drift != 0.0f) return;                             // per-symbol frequencies: k_sync_freqs
+    const int t = threadIdx.x, g = t / SF_GROUP, sym = t - g * SF_GROUP;
+    const int fi = g < 2 ? g : g + 1;
+    const float *ip = I + (size_t)job.cap * stride, *qp = Q + (size_t)job.cap * stride;
+    const int shift = job.shift;
+    for (int m = t; m < 4 * 2 * SPS; m += SF_THREADS) {
+        const int gg = m / (2 * SPS), f = gg < 2 ? gg : gg + 1;
+        tab[m] = tabs[((size_t)blockIdx.x * NFREQ1 + f) * (2 * SPS) + (m - gg * 2 * SPS)];
+    }
+    // staging: element e of a chunk = (symbol e / 8, sample e % 8)
+    constexpr int PER = (NSYM * SF_CHUNK + SF_THREADS - 1) / SF_THREADS;            // 2
+    float2 stage[PER];
+    auto fetch = [&](int c) {
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int e = t + u * SF_THREADS;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (e < NSYM * SF_CHUNK) {
+                const int k = shift + (e / SF_CHUNK) * SPS + c * SF_CHUNK + (e % SF_CHUNK);
+                if (k > 0 && k < np) v = make_float2(ip[k], qp[k]);                 // (:199)
+            }
+            stage[u] = v;
+        }
+    };
+    auto park = [&](int b) {
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int e = t + u * SF_THREADS;
+            if (e < NSYM * SF_CHUNK) buf[(b * NSYM + e / SF_CHUNK) * SF_PITCH + (e % SF_CHUNK)] = stage[u];
+        }
+    };
+    fetch(0);
+    park(0);
+    __syncthreads();
+    const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab + g * 2 * SPS);
+    pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
+    for (int c = 0; c < SPS / SF_CHUNK; c++) {
+        if (c + 1 < SPS / SF_CHUNK) fetch(c + 1);
+        if (sym < NSYM) {
+            const float2 *bp = buf + ((c & 1) * NSYM + sym) * SF_PITCH;
+#pragma unroll
+            for (int r = 0; r < SF_CHUNK; r++) {
+                const float2 v = bp[r];
+                const pk2 x = pk_make(v.x, v.x), y = pk_make(v.y, v.y), n = pk_make(-v.x, -v.x);
+                const ulonglong2 w01 = tp[c * SF_CHUNK + r], w23 = tp[SPS + c * SF_CHUNK + r];
+                ai01 = pk_add(pk_add(ai01, pk_mul(x, w01.x, negzero), one), pk_mul(y, w01.y, negzero), one);
+                aq01 = pk_add(pk_add(aq01, pk_mul(n, w01.y, negzero), one), pk_mul(y, w01.x, negzero), one);
+                ai23 = pk_add(pk_add(ai23, pk_mul(x, w23.x, negzero), one), pk_mul(y, w23.y, negzero), one);
+                aq23 = pk_add(pk_add(aq23, pk_mul(n, w23.y, negzero), one), pk_mul(y, w23.x, negzero), one);
+            }
+        }
+        if (c + 1 < SPS / SF_CHUNK) park((c + 1) & 1);
+        __syncthreads();
+    }
+    if (sym < NSYM) {
+        Acc8 a;
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
+        P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + sym] = acc_power(a);
+    }
 }
 
 // soft symbols from the four tone magnitudes of one (frequency, lag) (:216-225,243-256) followed by the caller's
@@ -845,6 +926,9 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
     k_tables<<<(njobs * NFREQ1 * 4 + 127) / 128, 128, 0, st>>>(jobs, job_list, njobs, tabs, 1);
     LAUNCHED();
     k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
+    LAUNCHED();
+    fano_attrs();                                             // (also opts k_sync_freqs_shared in to its dynamic shared memory)
+    k_sync_freqs_shared<<<njobs, SF_THREADS, SF_SMEM_BYTES, st>>>(I, Q, jobs, job_list, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
     LAUNCHED();
@@ -1450,6 +1534,7 @@ static void fano_attrs() {
     cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
     // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)
     const char *e = getenv("WSPR_CARVEOUT");
     const char mode = e ? e[0] : 'd';

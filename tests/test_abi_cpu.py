@@ -225,8 +225,8 @@ def test_packed_products_and_sums_are_not_contracted():
             count[cur] = count.get(cur, 0) + 1
     # packed multiply-accumulates per sample (4 tones x {i,q} x 2 products / 2 lanes = 8; low-pass: 4 outputs) x samples
     # (taps) in the unrolled loop body x 2 instructions each
-    expected = {"k_sync_lags": 8 * 16 * 2, "k_sync_freqs": 8 * 8 * 2, "k_jitter_soft": 8 * 8 * 2, "k_sync_generic": 8 * 8 * 2,
-                "k_sub_lpf": 4 * 8 * 2}
-    for name, n in expected.items():
+    expected = {"k_sync_lagsE": 8 * 16 * 2, "k_sync_freqsE": 8 * 8 * 2, "k_sync_freqs_sharedE": 8 * 8 * 2, "k_jitter_softE": 8 * 8 * 2,
+                "k_sync_genericE": 8 * 8 * 2, "k_sub_lpfI": 4 * 8 * 2}
+    for name, n in expected.items():                     # (mangled names: the suffix keeps k_sync_freqs and ..._shared apart)
         got = sum(v for k, v in count.items() if name in k)
         assert got == n, (name, got, n)
