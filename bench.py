@@ -265,7 +265,7 @@ def run_ours(args):
                     "traffic_source": "ncu --set full, profiles/r1_ncu_full_packed.txt, scaled to the mean candidates per launch",
                     "peak_source": peak_src,
                     "launches": sync_launches, "avg_launch_ms": round(sync_ms / max(sync_launches, 1), 4),
-                    "note": "FP32-issue bound, not HBM bound: %.2f TFLOP/s unfused fp32 (%.3g flop per candidate)"
+                    "note": "FP32-pipe bound, not HBM bound: %.2f TFLOP/s unfused fp32 as packed FFMA2 pairs (%.3g flop per candidate; ncu: 82 %% FMA-pipe active)"
                             % (candidates * SYNC_FLOP_PER_CANDIDATE / (sync_ms * 1e-3) / 1e12, SYNC_FLOP_PER_CANDIDATE)}
     whole_job_gbs = world * ncap * args.steps * BYTES_PER_CAPTURE / (total_ms * 1e-3) / 1e9
 
