@@ -72,6 +72,8 @@ struct SideSlot {
     bool busy = false;
     int *list = nullptr;           // [maxcap] deferred capture indices of one round
     int *count = nullptr;          // device counter of the list
+    int *list2 = nullptr;          // [chain_cap] the ones whose jitter-0 attempt failed (filled on the device)
+    int *count2 = nullptr;
     ChainScratch *scratch = nullptr;   // [chain_cap] soft symbols of the attempts of the parked candidates
     int chain_cap = 0;
 };
@@ -119,7 +121,7 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (SideSlot &s : c->side) {
-        void *sp[] = {s.list, s.count, s.scratch};
+        void *sp[] = {s.list, s.count, s.scratch, s.list2, s.count2};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (s.done) cudaEventDestroy(s.done);
@@ -192,6 +194,8 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
         CK(dalloc(&s.count, 1));
         s.chain_cap = std::max(8, std::min(maxcap, 1024));
         CK(dalloc(&s.scratch, (size_t)s.chain_cap));
+        CK(dalloc(&s.list2, (size_t)s.chain_cap));
+        CK(dalloc(&s.count2, 1));
     }
     HostTables t;
     host_tables(t);
@@ -449,7 +453,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 c->deferred += ndefer;
                 for (int off = 0; off < ndefer; off += side->chain_cap)   // (more than chain_cap parked at once: in turn)
                     launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list + off, std::min(side->chain_cap, ndefer - off),
-                                    side->scratch, c->stats, p, side->st);
+                                    side->scratch, side->list2, side->count2, c->stats, p, side->st);
                 CK(cudaEventRecord(side->done, side->st));
                 side->busy = true;
             }

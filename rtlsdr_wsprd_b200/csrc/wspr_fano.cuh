@@ -77,16 +77,19 @@ struct FanoGmem {
     }
 };
 
-struct FanoNoStop {                    // hook: stop() polled every 256 trips by active lanes, success() called on a decode
+// hook: stop() polled every 256 trips by active lanes; success() called by a lane the moment it decodes, with its cycle
+// count and the means to read the decoded bytes (byte b = the low byte of the encoder state stored with node 7 + 8 b)
+struct FanoNoStop {
     __device__ bool stop() const { return false; }
-    __device__ void success() const {}
+    template <typename Mem>
+    __device__ void success(unsigned, const Mem &, unsigned) const {}
 };
 
 // Every lane of the warp must call this together.  `want`: this lane has an attempt to decode (symbols valid).
 // mem: this warp's FANO_WARP_SMEM_BYTES of scratch, FanoSmem{cvta'd shared address} or FanoGmem{pointer}.
 // stop_after: 0 = run to the reference's limit; else give up (FANO_STOPPED) once that many cycles were spent.
 // hook.stop(): evaluated every 256 trips by active lanes, true abandons the attempt (FANO_STOPPED);
-// hook.success(): called by a lane the moment it decodes.
+// hook.success(cycles, mem, node_base): called by a lane the moment it decodes.
 // A lane that has finished keeps executing the (uniform) loop as a harmless zombie -- its threshold is parked so high
 // that it only ever tightens it in place -- while its result waits in separate registers; the hot loop therefore
 // carries no per-lane "active" predicate.
@@ -230,7 +233,7 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
                 r_metric = (unsigned)gam;
                 r_cycles = (it > limit) ? limit + 2u : it + 1u;   // (it > limit: a lane past the limit, not yet noticed)
                 r_maxnp = (unsigned)maxnp;
-                if (r_rc == 0) hook.success();
+                if (r_rc == 0) hook.success(r_cycles, mem, node_base);
             }
             pos = nbits - 1;                       // park: stay put, tightening an unreachable threshold
             thr = PARKED;

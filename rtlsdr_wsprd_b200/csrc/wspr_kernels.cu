@@ -944,7 +944,27 @@ struct ChainStop {                                             // abandon an att
     int *best;
     int idt;
     __device__ bool stop() const { return *(const volatile int *)best < idt; }
-    __device__ void success() const { atomicMin(best, idt); }
+    template <typename Mem>
+    __device__ void success(unsigned, const Mem &, unsigned) const { atomicMin(best, idt); }
+};
+// jitter-0 attempt of a parked candidate, one candidate per lane (k_chain_first): a decode hands the capture back to the
+// rounds at once, without waiting for the other 31 candidates of the warp
+struct FirstHook {
+    Job *job;
+    CapState *cs;
+    int *stats;
+    __device__ bool stop() const { return false; }
+    template <typename Mem>
+    __device__ void success(unsigned cycles, const Mem &mem, unsigned node_base) const {
+        for (int b = 0; b < 12; b++) job->dec[b] = 0;
+        for (int b = 0; b < (NBITS >> 3); b++) job->dec[b] = (unsigned char)mem.ld(node_base + mem.row * (unsigned)(7 + 8 * b)).x;
+        job->cycles = cycles;
+        job->decoded = 1;
+        job->idt = 0;
+        atomicAdd(stats + 0, 1);
+        __threadfence();
+        *(volatile int *)&cs->phase = PH_RESOLVE;
+    }
 };
 static void fano_attrs();
 
@@ -1022,11 +1042,13 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 // stats: [0] settled by the full-budget jitter-0 run, [1] by a jittered attempt, [2] never decoded
 __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
                                                      const Job *__restrict__ jobs, const Attempt *__restrict__ att0,
-                                                     const int *__restrict__ defer_list, ChainScratch *__restrict__ scratch,
-                                                     int np, int stride, float minrms, int symfac, pk2 negzero, pk2 one) {
+                                                     const int *__restrict__ defer_list, const int *__restrict__ count,
+                                                     int skip0, ChainScratch *__restrict__ scratch, int np, int stride,
+                                                     float minrms, int symfac, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float4 P[NSYM];
     const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
+    if (count && e >= *count) return;                          // (list filled on the device: the grid is sized for the worst case)
     const int cap = defer_list[e];
     const Job &job = jobs[cap];
     ChainScratch &cs = scratch[e];
@@ -1034,7 +1056,7 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
         const Attempt &a = att0[cap];
         for (int i = t; i < NSYM; i += 192) cs.sym[0][i] = a.sym[i];
         if (t == 0) {
-            cs.gate[0] = a.gate && a.unfinished;
+            cs.gate[0] = !skip0 && a.gate && a.unfinished;   // (skip0: the jitter-0 attempt has already been run to the end)
             cs.best = NJIT;                                    // no attempt has decoded yet
             cs.done = 0;
         }
@@ -1069,9 +1091,13 @@ constexpr int CHAIN_PIECES = 2;
 __global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
                                                                  const int *__restrict__ defer_list,
                                                                  ChainScratch *__restrict__ scratch, int n, int npieces,
-                                                                 int nattempts, int delta, unsigned maxcycles,
-                                                                 int *__restrict__ stats) {
+                                                                 const int *__restrict__ count, int nattempts, int delta,
+                                                                 unsigned maxcycles, int *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char fano_smem_all[];
+    if (count) {                                               // list filled on the device: the grid is sized for the worst case
+        n = *count;
+        npieces = n + (nattempts > 32 ? (n + 1) / 2 : 0);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int piece = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
     if (piece >= npieces) return;
@@ -1123,25 +1149,71 @@ __global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restric
     }
 }
 
+// Two-stage form of the parked candidates (WSPR_CHAIN_STAGES=2, off by default).  Stage 1: the jitter-0 attempts with the
+// full budget, ONE CANDIDATE PER LANE (32 per warp).  Most parked candidates (78 % on the config-3 corpus) decode here,
+// after 4 096 .. 810 000 cycles; the single-stage form gives each of them its own 1.5 warps for all 43 attempts, i.e.
+// ~1 200 one-warp CTAs per batch resident for as long as their jitter-0 run takes.  A candidate that decodes is handed
+// back at once (FirstHook); the others are appended to list2 for stage 2 (the 42 jittered attempts, k_jitter_soft +
+// k_chain_fano with attempt 0 masked), or, in quick mode, handed back undecoded.
+// Measured: results identical (GPU suite green with it), 4 % SLOWER end to end -- a candidate that needs the jitter
+// search now waits for the slowest jitter-0 attempt of its whole round before its 42 attempts even start (88 rounds per
+// batch instead of 66), and that latency costs more than the shorter residence gains.
+__global__ void __launch_bounds__(32) k_chain_first(Job *__restrict__ jobs, CapState *__restrict__ caps,
+                                                    const Attempt *__restrict__ att0, const int *__restrict__ defer_list, int n,
+                                                    int delta, unsigned maxcycles, int quick, int *__restrict__ list2,
+                                                    int *__restrict__ count2, int *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char fano_smem[];
+    const int e = (int)blockIdx.x * 32 + (int)threadIdx.x;
+    const bool mine = e < n;
+    const int cap = mine ? defer_list[e] : defer_list[0];
+    const Attempt &a = att0[cap];
+    const bool want = mine && a.gate && a.unfinished;         // (else the attempt already ran to its end in the round, or is gated off)
+    Job &job = jobs[cap];
+    FanoResult r;
+    fano_dense<false>(r, want, a.sym, &c_mettab[0][0], delta, maxcycles, 0, FirstHook{&job, &caps[cap], stats},
+                      FanoSmem::at(fano_smem, 512u));
+    if (!mine || (want && r.rc == 0)) return;                  // (a decode has been published by the hook)
+    if (want) job.cycles = r.cycles;                           // `cycles` keeps the last completed decoder call's count
+    if (quick) {                                               // wsprd.c:764-765: no jitter search, the candidate is done
+        atomicAdd(stats + 2, 1);
+        __threadfence();
+        *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+    } else {
+        list2[atomicAdd(count2, 1)] = cap;
+    }
+}
+
 void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st) {
+                     ChainScratch *scratch, int *list2, int *count2, int *stats, const DecodeParams &p, cudaStream_t st) {
     if (n <= 0) return;
     fano_attrs();
     const int nattempts = p.quickmode ? 1 : NJIT;
-    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, scratch, p.np, p.stride, p.minrms, p.symfac, PK_NEGZERO,
-                                                      PK_ONE);
-    LAUNCHED();
-    const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
     // WSPR_DEBUG_CHAIN_MAXCYCLES: experiment knob (wrong results!) to measure what the long Fano runs cost
     static const unsigned dbg_maxcycles = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
-    // WSPR_CHAIN_PIECES: experiment knob (2 = two pieces per CTA)
+    // WSPR_CHAIN_PIECES: experiment knob (2 = two pieces per CTA); WSPR_CHAIN_STAGES=2: jitter-0 attempts first, 32 candidates
+    // per warp (k_chain_first), the 42 jittered attempts only for the candidates that fail it
     static const int ppc = [] { const char *e = getenv("WSPR_CHAIN_PIECES"); int v = e ? atoi(e) : 1; return v >= 1 && v <= CHAIN_PIECES ? v : 1; }();
+    static const bool two_stage = [] { const char *e = getenv("WSPR_CHAIN_STAGES"); return e && e[0] == '2'; }();
+    const unsigned maxcycles = dbg_maxcycles ? dbg_maxcycles : p.maxcycles;
+    const int *count = nullptr;
+    if (two_stage) {
+        cudaMemsetAsync(count2, 0, sizeof(int), st);
+        k_chain_first<<<(n + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, att0, defer_list, n, p.delta, maxcycles, p.quickmode,
+                                                                      list2, count2, stats);
+        LAUNCHED();
+        if (p.quickmode) return;
+        defer_list = list2;                                    // stage 2: the candidates whose jitter-0 attempt failed
+        count = count2;
+    }
+    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, count, two_stage ? 1 : 0, scratch, p.np, p.stride,
+                                                      p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
+    LAUNCHED();
+    const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
     k_chain_fano<<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
-        jobs, caps, defer_list, scratch, n, nctas, nattempts, p.delta, dbg_maxcycles ? dbg_maxcycles : p.maxcycles, stats);
+        jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
     LAUNCHED();
 }
 
-// stand-alone Fano batches for the C-ABI test hook wspr_fano_batch(): 32 attempts per warp, or (solo) one per warp
 __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restrict__ symbols, int n, int delta,
                                                   unsigned maxcycles, unsigned stop_after, int solo, int *__restrict__ rc,
                                                   unsigned *__restrict__ metric, unsigned *__restrict__ cycles,
@@ -1533,6 +1605,7 @@ static void fano_attrs() {
     if (done.load()) return;
     cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_first, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
     // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)

@@ -159,8 +159,9 @@ void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const Deco
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
                     int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st);
 // side-stream completion of deferred candidates: full-budget jitter-0 Fano, then the jitter search (wsprd.c:741-766)
+// list2 / count2: device list (n entries) and counter for the candidates that go on to the jitter search
 void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *stats, const DecodeParams &p, cudaStream_t st);
+                     ChainScratch *scratch, int *list2, int *count2, int *stats, const DecodeParams &p, cudaStream_t st);
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
                     const DecodeParams &p, cudaStream_t st);
 void launch_subtract(float *I, float *Q, const CapState *caps, const int *sub_list, int nsub_max, const Counters *cnt,
