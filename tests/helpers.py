@@ -50,6 +50,26 @@ def spot_lines(r):
     return [po.spot_line(x) for x in r]
 
 
+# a hashtable.txt found on entry: existing entries, one the first call overwrites, an out-of-range one, garbage
+HASHTABLE_SEED_FILE = "   17 ZZ9ZZZ AA00\n40000 BAD\n  junk\n 5970 OLDCALL\n"
+
+
+def spots_match_golden(r, gold_spots, line_fn):
+    """Every field of a RESULT_DTYPE array against the JSON form written by tools/make_golden*.py (floats as hex)."""
+    if len(r) != len(gold_spots):
+        return False
+    for x, y in zip(r, gold_spots):
+        if (x["message"].decode(), x["call"].decode(), x["loc"].decode(), x["pwr"].decode()) != \
+                (y["message"], y["call"], y["loc"], y["pwr"]):
+            return False
+        if (float(x["freq"]).hex(), float(x["snr"]).hex(), float(x["dt"]).hex(), float(x["sync"]).hex()) != \
+                (y["freq"], y["snr"], y["dt"], y["sync"]):
+            return False
+        if (float(x["drift"]), int(x["jitter"]), int(x["cycles"]), line_fn(x)) != (y["drift"], y["jitter"], y["cycles"], y["line"]):
+            return False
+    return True
+
+
 def hashtable_scenario():
     """Three captures for the persistent-hashtable option (reference -H, wsprd.c:481-494,842-852): A teaches the table a
     type-1 and a type-2 callsign, B refers to them (and to an unknown one) by hash in type-3 messages, then A again."""

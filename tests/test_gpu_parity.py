@@ -289,13 +289,19 @@ def test_persistent_hashtable_option():
     """options.usehashtable (reference -H, wsprd.c:481-494,842-852) through the reference entry point: spots and the
     hashtable.txt left in the CWD after every call identical to the oracle's."""
     opt_o, opt_g = po.default_options(usehashtable=1), w.default_options(usehashtable=1)
-    seed = "   17 ZZ9ZZZ AA00\n40000 BAD\n  junk\n 5970 OLDCALL\n"
+    seed = H.HASHTABLE_SEED_FILE
     want = H.run_hashtable_scenario(lambda i, q: po.decode(po.oracle(), i, q, opt_o, cwd_scratch=False)[0], seed)
     got = H.run_hashtable_scenario(lambda i, q: w.wspr_decode(i, q, options=opt_g), seed)
     assert any(b"<K1JT>" in x["message"] for x in got[1][0]) and any(b"<...>" in x["message"] for x in got[1][0])
     for (ra, fa), (rb, fb) in zip(want, got):
         assert H.results_equal(ra, rb), H.diff_results(ra, rb)
         assert fa == fb, (fa, fb)
+    # and identical to what the compiled reference produced (tests/golden/golden_hashtable.json)
+    with open(os.path.join(H.GOLDEN, "golden_hashtable.json")) as f:
+        gold = json.load(f)
+    assert gold["seed_file"] == seed and len(gold["calls"]) == len(got)
+    for (rb, fb), g in zip(got, gold["calls"]):
+        assert H.spots_match_golden(rb, g["spots"], w.spot_line) and fb == g["hashtable_txt"]
     # without the option nothing is read or written and hashed calls stay unresolved
     i, q = H.hashtable_scenario()[1]
     r = w.wspr_decode(i.copy(), q.copy())

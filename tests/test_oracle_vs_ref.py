@@ -191,7 +191,7 @@ def test_persistent_hashtable_option_matches_reference():
     if not po.ref_available():
         pytest.skip("compiled reference not available")
     opt = po.default_options(usehashtable=1)
-    seed = "   17 ZZ9ZZZ AA00\n40000 BAD\n  junk\n 5970 OLDCALL\n"      # existing entries, an out-of-range one, garbage
+    seed = H.HASHTABLE_SEED_FILE
     runs = {}
     for name, lib in (("ref", po.ref()), ("oracle", po.oracle())):
         runs[name] = H.run_hashtable_scenario(lambda i, q: po.decode(lib, i, q, opt, cwd_scratch=False)[0], seed)
@@ -201,3 +201,17 @@ def test_persistent_hashtable_option_matches_reference():
         assert H.results_equal(ra, rb), H.diff_results(ra, rb)
         assert fa == fb
     assert "   17 ZZ9ZZZ AA00" in runs["ref"][0][1] and " 5970 W1AW FN31" in runs["ref"][0][1]
+
+
+def test_persistent_hashtable_option_matches_committed_golden():
+    """The same scenario against tests/golden/golden_hashtable.json (generated from the compiled reference by
+    tools/make_golden_hashtable.py), so that the pin also holds where /root/reference is absent."""
+    with open(os.path.join(H.GOLDEN, "golden_hashtable.json")) as f:
+        gold = json.load(f)
+    assert gold["seed_file"] == H.HASHTABLE_SEED_FILE
+    opt = po.default_options(usehashtable=1)
+    runs = H.run_hashtable_scenario(lambda i, q: po.decode(po.oracle(), i, q, opt, cwd_scratch=False)[0], gold["seed_file"])
+    assert len(runs) == len(gold["calls"]) == 3
+    for (r, txt), g in zip(runs, gold["calls"]):
+        assert H.spots_match_golden(r, g["spots"], po.spot_line), ([x["message"] for x in r], [y["message"] for y in g["spots"]])
+        assert txt == g["hashtable_txt"]
