@@ -140,7 +140,7 @@ double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
  * counterpart of fano() (wsprd/fano.h:14-28; metric table = the one wspr_decode builds, wsprd.c:467-473).  stop_after != 0
  * cuts a run short after that many cycles (rc 2); solo bit 0: one attempt per warp instead of 32; bit 1: tree state in global
  * memory; bit 2: the instantiation the decode kernels use (time-out test every 256 trips, maxnp not tracked: rc, cycles and
- * data as fano.c's, metric too for successful decodes).
+ * data as fano.c's, metric too for successful decodes); bit 3: the experimental pipelined loop (WSPR_FANO_PIPE).
  * rc/metric/cycles/maxnp: n entries each, data: n x 12 bytes (host memory); clocks (may be NULL): SM clock ticks each
  * attempt took. */
 int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,

@@ -109,7 +109,7 @@ struct FanoNoStop {
 // for a trip of 81 instructions -- the trip is bound by the DEPTH of its predicate/select dataflow, not by issue slots
 // and not by the shared-memory latency: holding the two records in registers and fetching the successors' records one
 // trip ahead (three loads in flight across the loop edge, 111 instructions) was slower, 263 clocks per cycle.
-template <bool EXACT, bool SMALLSTEP, typename Hook, typename Mem>
+template <bool EXACT, bool SMALLSTEP, bool PIPE, typename Hook, typename Mem>
 __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
                                                 const short *__restrict__ mettab, int delta, unsigned maxcycles,
                                                 unsigned stop_after, Hook hook, Mem mem) {
@@ -151,6 +151,13 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
     int cur = fano_tm0(w);                         // metric of the branch being tried
     int r_rc = -1;                                 // result registers, filled when the lane finishes
     unsigned r_metric = 0, r_cycles = 0, r_maxnp = 0;
+    // PIPE: the two records of the node a trip stands on are fetched during the PREVIOUS trip, as soon as that trip knows
+    // where it moves to (see below); they are carried in registers.
+    uint4 nl_c = make_uint4(0u, 0u, 0u, 0u), nd_c = make_uint4(0u, 0u, 0u, 0u);
+    if (PIPE) {
+        nl_c = mem.ld(lvl_base + row);
+        nd_c = mem.ld(node_base - row);             // (the root has no parent: never used)
+    }
 #pragma unroll 1
     for (unsigned trip = 0;; trip++) {
         if ((trip & 255u) == 0u) {                 // housekeeping
@@ -171,15 +178,33 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
             }
             if (!__any_sync(0xffffffffu, act)) break;
         }
-        // speculative fetches: the level we would move down to, the node we would step back to (never used at the root,
-        // where the address below is the last level record)
-        const uint4 nl = mem.ld(lvl_base + row * (unsigned)(pos + 1));
-        const uint4 nd = mem.ld(node_base + row * (unsigned)pos - row);
+        // the level we would move down to, the node we would step back to (never used at the root, where that address is
+        // the last level record)
+        uint4 nl, nd;
+        if (PIPE) {
+            nl = nl_c;
+            nd = nd_c;
+        } else {
+            nl = mem.ld(lvl_base + row * (unsigned)(pos + 1));
+            nd = mem.ld(node_base + row * (unsigned)pos - row);
+        }
         const int ng = gam + cur;
         const bool newc = !inback;                 // this trip opens a new Fano cycle
         const bool fwd = newc && (ng >= thr);
         const bool tig = newc && !fwd && (pos == 0 || pgam < thr);
         const bool bck = !fwd && !tig;
+        // PIPE: which way the decoder moves depends on registers only, so the move is decided first, the node is pushed, and
+        // the records of the node it lands on are requested at once; everything below works on the records fetched a trip
+        // ago and the shared-memory latency overlaps with it instead of heading the loop-carried dependence chain.  (The
+        // push precedes the fetch in program order, so a forward move reads back the record it has just written.)
+        int posN = pos + (fwd ? 1 : (bck ? -1 : 0));
+        const bool arrived = posN == nbits;          // a move past the last node: decoded, the lane parks where it stands
+        posN = arrived ? nbits - 1 : posN;
+        if (PIPE) {
+            if (fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w, (unsigned)pgam);
+            nl_c = mem.ld(lvl_base + row * (unsigned)(posN + 1));
+            nd_c = mem.ld(node_base + row * (unsigned)posN - row);
+        }
         if (EXACT && newc && it >= limit && act) {  // the reference's loop ends here: time-out (rare, once per lane)
             act = false;
             r_rc = -1;
@@ -201,7 +226,7 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
             k -= (k * delta > d) ? 1 : 0;
             thrF = thr + k * delta;
         }
-        if (fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w, (unsigned)pgam);
+        if (!PIPE && fwd) mem.st(node_base + row * (unsigned)pos, enc, (unsigned)gam, w, (unsigned)pgam);
         const unsigned e = enc << 1;
         const bool pa = (__popc(e & POLY_A) & 1) != 0, pb = (__popc(e & POLY_B) & 1) != 0;   // branch symbol = 2*pa + pb
         const unsigned wlo = pb ? nl.y : nl.x, whi = pb ? nl.w : nl.z;
@@ -225,8 +250,8 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
         w = fwd ? wF : (bck ? wB : (w & 0x7fffffffu));
         cur = ((int)w < 0) ? fano_tm1(w) : fano_tm0(w);
         inback = bck && !b1 && !b2;
-        pos += fwd ? 1 : (bck ? -1 : 0);
-        if (pos == nbits) {                        // reached the last node: decoded (rare, once per lane)
+        pos = posN;
+        if (arrived) {                             // reached the last node: decoded (rare, once per lane)
             if (act) {
                 act = false;
                 r_rc = (it >= limit) ? -1 : 0;     // (a decode in the very last cycle counts as a timeout, fano.c:234)
@@ -235,8 +260,7 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
                 r_maxnp = (unsigned)maxnp;
                 if (r_rc == 0) hook.success(r_cycles, mem, node_base);
             }
-            pos = nbits - 1;                       // park: stay put, tightening an unreachable threshold
-            thr = PARKED;
+            thr = PARKED;                          // park: stay put (pos = nbits - 1), tightening an unreachable threshold
             inback = false;
         }
     }
@@ -252,12 +276,12 @@ __device__ __forceinline__ void fano_dense_impl(FanoResult &out, bool want, cons
     }
 }
 
-template <bool EXACT, typename Hook, typename Mem>
+template <bool EXACT, bool PIPE = false, typename Hook, typename Mem>
 __device__ __forceinline__ void fano_dense(FanoResult &out, bool want, const unsigned char *__restrict__ symbols,
                                            const short *__restrict__ mettab, int delta, unsigned maxcycles, unsigned stop_after,
                                            Hook hook, Mem mem) {
-    if (delta > 10) fano_dense_impl<EXACT, true>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
-    else fano_dense_impl<EXACT, false>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
+    if (delta > 10) fano_dense_impl<EXACT, true, PIPE>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
+    else fano_dense_impl<EXACT, false, PIPE>(out, want, symbols, mettab, delta, maxcycles, stop_after, hook, mem);
 }
 
 }  // namespace wspr

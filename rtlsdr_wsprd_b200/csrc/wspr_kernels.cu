@@ -1088,6 +1088,9 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
 // the bulk kernels is per SM rather than per warp, so parked work should sit on half as many SMs: 9 % slower end to end
 // -- a 170 KB CTA has to wait for a nearly empty SM and then excludes everything else from it.
 constexpr int CHAIN_PIECES = 2;
+// PIPE: the pipelined form of the decoder loop (wspr_fano.cuh), selected with WSPR_FANO_PIPE=1 -- checked against the oracle
+// on the host (tests/test_fano_host.py) and through wspr_fano_batch on the GPU, not yet the default.
+template <bool PIPE>
 __global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
                                                                  const int *__restrict__ defer_list,
                                                                  ChainScratch *__restrict__ scratch, int n, int npieces,
@@ -1115,8 +1118,8 @@ __global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restric
     const bool want = mine && cs.gate[idt];
     FanoResult r;
     ChainStop stop{&cs.best, idt};
-    fano_dense<false>(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
-               FanoSmem::at(fano_smem, 512u));
+    fano_dense<false, PIPE>(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
+                            FanoSmem::at(fano_smem, 512u));
     if (mine) {
         cs.ok[idt] = want && (r.rc == 0);
         cs.unfinished[idt] = want && (r.rc == FANO_STOPPED);
@@ -1209,8 +1212,13 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, C
                                                       p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
-    k_chain_fano<<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
-        jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
+    static const bool pipe = [] { const char *e = getenv("WSPR_FANO_PIPE"); return e && e[0] == '1'; }();
+    if (pipe)
+        k_chain_fano<true><<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
+            jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
+    else
+        k_chain_fano<false><<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
+            jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
     LAUNCHED();
 }
 
@@ -1220,7 +1228,7 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
                                                   unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
                                                   unsigned long long *__restrict__ clocks, unsigned char *__restrict__ gmem) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
-    const bool fast = (solo & 4) != 0;
+    const bool fast = (solo & 4) != 0, pipe = (solo & 8) != 0;
     solo &= 3;
     const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * 32 + threadIdx.x);
     const bool want = i < n && (!solo || threadIdx.x == 0);
@@ -1230,6 +1238,12 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
     if (gmem)
         fano_dense<true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
                          FanoGmem{gmem + (size_t)blockIdx.x * FANO_WARP_SMEM_BYTES, 512u});
+    else if (fast && pipe)
+        fano_dense<false, true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                                FanoSmem::at(fano_smem, 512u));
+    else if (pipe)
+        fano_dense<true, true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
+                               FanoSmem::at(fano_smem, 512u));
     else if (fast)                                             // the instantiation the decode kernels use
         fano_dense<false>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
                           FanoSmem::at(fano_smem, 512u));
@@ -1251,7 +1265,7 @@ void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned m
     if (n <= 0) return;
     fano_attrs();
     const int blocks = (solo & 1) ? n : (n + 31) / 32;
-    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 5, rc, metric,
+    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 13, rc, metric,
                                                                    cycles, maxnp, data, clocks, gmem);
     LAUNCHED();
 }
@@ -1606,7 +1620,8 @@ static void fano_attrs() {
     cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_chain_first, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chain_fano<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
     cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
     // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)
     const char *e = getenv("WSPR_CARVEOUT");
@@ -1617,7 +1632,8 @@ static void fano_attrs() {
     if (mode == 'c' || mode == 'm' || numeric) {
         cudaFuncSetAttribute(k_fano_round, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(k_fano_test, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_chain_fano, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_chain_fano<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_chain_fano<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     }
     if (mode == 'm' || numeric) {
         cudaFuncSetAttribute(k_jitter_soft, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
