@@ -136,11 +136,18 @@ float wspr_ctx_last_sync_ms(wspr_ctx *ctx);
 int wspr_ctx_last_sync_launches(wspr_ctx *ctx);
 double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
 
+/* Counters of the per-device pool of Fano worker warps that finishes parked candidates (wsprd.c:741-766 when fano() does
+ * not converge at once): out8[0] worker warps allowed, [1] SMs set aside for them (0: they share the SMs with the other
+ * kernels), [2] housekeeping periods (256 decoder-loop trips) worker warps were alive for, [3] lane-periods with an attempt
+ * in the lane (utilisation = [3] / (32 x [2])), [4] attempts decoded to their end, [5] attempts skipped or abandoned,
+ * [6] worker warps started.  device -1: the current device; reset != 0 clears the counters. */
+int wspr_fano_stats(int device, unsigned long long *out8, int reset);
+
 /* the Fano decoder kernel (K5) on caller-supplied soft symbols: n vectors of 162 deinterleaved bytes, the batch / device
  * counterpart of fano() (wsprd/fano.h:14-28; metric table = the one wspr_decode builds, wsprd.c:467-473).  stop_after != 0
- * cuts a run short after that many cycles (rc 2); solo bit 0: one attempt per warp instead of 32; bit 1: tree state in global
- * memory; bit 2: the instantiation the decode kernels use (time-out test every 256 trips, maxnp not tracked: rc, cycles and
- * data as fano.c's, metric too for successful decodes); bit 3: the experimental pipelined loop (WSPR_FANO_PIPE).
+ * cuts a run short after that many cycles (rc 2); solo bit 0: one attempt per warp instead of 32; bit 2: the instantiation
+ * the decode kernels use (time-out test every 256 trips, maxnp not tracked: rc, cycles and data as fano.c's, metric too for
+ * successful decodes).
  * rc/metric/cycles/maxnp: n entries each, data: n x 12 bytes (host memory); clocks (may be NULL): SM clock ticks each
  * attempt took. */
 int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,

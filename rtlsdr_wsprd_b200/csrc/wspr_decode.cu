@@ -7,15 +7,19 @@
 // *rounds*: each round advances every ready capture by one candidate (sync search -> soft symbols -> budgeted Fano
 // -> unpack/resolve -> subtraction) and runs the pass set-up (spectrogram, candidate search, coarse sync) for the
 // captures that enter a new pass.  The rare candidates that need a long Fano run or the 42-attempt jitter search
-// are finished on side streams while the rounds go on, so a straggler delays only its own capture.
+// are finished by a per-device pool of Fano worker warps while the rounds go on, so a straggler delays only its own capture.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <sched.h>
+#include <unistd.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,26 +68,149 @@ static void host_tables(HostTables &t) {
     t.floor_snr = 0.1 * t.min_snr;                                                // wsprd.c:595
 }
 
-constexpr int NSIDE = 12;          // side-stream slots for deferred candidates
+// ---- per-device Fano service --------------------------------------------------------------------------------------
+// The long Fano runs of parked candidates (wsprd.c:741-766 when the decoder does not converge at once) are served by ONE pool
+// of worker warps per GPU, fed from a device-side queue that every context of the process pushes to (wspr_kernels.cu,
+// k_fano_workers).  Optionally the pool runs on its own SM partition (CUDA green contexts through the driver API; libcuda is
+// not linked, the entry points come from cudaGetDriverEntryPoint): the workers then never share an SM -- its issue slots, its
+// shared-memory carve-out -- with the bulk kernels, which get the remaining SMs.
+//   WSPR_FANO_SMS   SMs set aside for the pool (even; 0 = no partition, workers and bulk kernels share every SM)
+//   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
+//                   per SM unpartitioned)
+//   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
+// All are read once, when the first context on a device is created.
+#ifndef WSPR_DEFAULT_FANO_SMS
+#define WSPR_DEFAULT_FANO_SMS 0
+#endif
+#ifndef WSPR_DEFAULT_FANO_POOL_PER_SM
+#define WSPR_DEFAULT_FANO_POOL_PER_SM 2
+#endif
+constexpr int FANO_RING = 1 << 16;                 // candidates the queue can hold
+constexpr int NFANO_STREAMS = 4;
 
-struct SideSlot {
-    cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
-    bool busy = false;
-    int *list = nullptr;           // [maxcap] deferred capture indices of one round
-    int *count = nullptr;          // device counter of the list
-    int *list2 = nullptr;          // [chain_cap] the ones whose jitter-0 attempt failed (filled on the device)
-    int *count2 = nullptr;
-    ChainScratch *scratch = nullptr;   // [chain_cap] soft symbols of the attempts of the parked candidates
-    int chain_cap = 0;
+struct FanoService {
+    int device = -1;
+    int fano_sms = 0, pool = 0, total_sms = 0;
+    bool partitioned = false;
+    CUgreenCtx g_fano = nullptr, g_bulk = nullptr;
+    FanoQueue *queue = nullptr;                    // device
+    FanoQueueEntry *ring = nullptr;                // device
+    std::mutex mu;
+    std::vector<std::pair<size_t, ChainScratch *>> free_scratch;   // (records, memory) returned by destroyed contexts
+    std::string note;
 };
+static std::mutex g_svc_mu;
+static FanoService *g_svc[64] = {nullptr};
+
+template <class F>
+static F driver_entry(const char *name) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (F)fn;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// SM partition: `want` SMs for the Fano pool, the rest for everything else
+static bool fano_partition(FanoService *s, int want) {
+    auto pDeviceGet = driver_entry<CUresult (*)(CUdevice *, int)>("cuDeviceGet");
+    auto pGetRes = driver_entry<CUresult (*)(CUdevice, CUdevResource *, CUdevResourceType)>("cuDeviceGetDevResource");
+    auto pSplit = driver_entry<CUresult (*)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned)>(
+        "cuDevSmResourceSplitByCount");
+    auto pDesc = driver_entry<CUresult (*)(CUdevResourceDesc *, CUdevResource *, unsigned)>("cuDevResourceGenerateDesc");
+    auto pCreate = driver_entry<CUresult (*)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned)>("cuGreenCtxCreate");
+    if (!pDeviceGet || !pGetRes || !pSplit || !pDesc || !pCreate) return false;
+    CUdevice dev;
+    CUdevResource all, small, rest;
+    if (pDeviceGet(&dev, s->device) != CUDA_SUCCESS || pGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned ng = 1;
+    // (the default granularity on sm_100 is 8 SMs; IGNORE_SM_COSCHEDULING gives any even count -- no clusters are used here)
+    if (pSplit(&small, &ng, &all, &rest, CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING, (unsigned)want) != CUDA_SUCCESS || ng != 1) return false;
+    CUdevResourceDesc dsmall, drest;
+    if (pDesc(&dsmall, &small, 1) != CUDA_SUCCESS || pDesc(&drest, &rest, 1) != CUDA_SUCCESS) return false;
+    if (pCreate(&s->g_fano, dsmall, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (pCreate(&s->g_bulk, drest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    s->fano_sms = (int)small.sm.smCount;
+    return true;
+}
+
+// (the caller has made `device` current)
+static FanoService *fano_service(int device) {
+    std::lock_guard<std::mutex> lock(g_svc_mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (g_svc[device]) return g_svc[device];
+    FanoService *s = new FanoService();
+    s->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return nullptr; }
+    s->total_sms = prop.multiProcessorCount;
+    init_kernel_attributes();
+    const int want = env_int("WSPR_FANO_SMS", WSPR_DEFAULT_FANO_SMS);
+    if (want > 0 && want < s->total_sms) {
+        s->partitioned = fano_partition(s, want);
+        if (!s->partitioned) s->note = "SM partition unavailable (green contexts): Fano workers share the SMs";
+    }
+    if (!s->partitioned) s->fano_sms = 0;
+    const int per_sm = (228 * 1024) / (fano_warp_smem_bytes() + 1024);
+    s->pool = env_int("WSPR_FANO_POOL", s->partitioned ? s->fano_sms * per_sm : s->total_sms * WSPR_DEFAULT_FANO_POOL_PER_SM);
+    if (s->pool < 1) s->pool = 1;
+    FanoQueue h;
+    memset(&h, 0, sizeof h);
+    h.pool = s->pool;
+    h.per_sm = env_int("WSPR_FANO_PER_SM", 0);
+    h.mask = FANO_RING - 1;
+    if (cudaMalloc((void **)&s->ring, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||
+        cudaMemset(s->ring, 0, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||
+        cudaMalloc((void **)&s->queue, sizeof(FanoQueue)) != cudaSuccess) { delete s; return nullptr; }
+    h.ring = s->ring;
+    if (cudaMemcpy(s->queue, &h, sizeof h, cudaMemcpyHostToDevice) != cudaSuccess) { delete s; return nullptr; }
+    g_svc[device] = s;
+    return s;
+}
+
+static cudaError_t service_stream(FanoService *s, bool fano, cudaStream_t *out) {
+    if (s->partitioned) {
+        static auto pStream = driver_entry<CUresult (*)(CUstream *, CUgreenCtx, unsigned, int)>("cuGreenCtxStreamCreate");
+        CUstream st = nullptr;
+        if (!pStream || pStream(&st, fano ? s->g_fano : s->g_bulk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return cudaErrorUnknown;
+        *out = (cudaStream_t)st;
+        return cudaSuccess;
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+
+// ChainScratch records are leased from the service and never freed while the process runs (see wspr_kernels.cuh)
+static ChainScratch *lease_scratch(FanoService *s, size_t n) {
+    {
+        std::lock_guard<std::mutex> lock(s->mu);
+        for (size_t i = 0; i < s->free_scratch.size(); i++)
+            if (s->free_scratch[i].first >= n) {
+                ChainScratch *p = s->free_scratch[i].second;
+                s->free_scratch.erase(s->free_scratch.begin() + i);
+                return p;
+            }
+    }
+    ChainScratch *p = nullptr;
+    if (cudaMalloc((void **)&p, n * sizeof(ChainScratch)) != cudaSuccess) return nullptr;
+    // next >= nattempts in every record: nothing to claim until a candidate is parked there
+    if (cudaMemset(p, 0, n * sizeof(ChainScratch)) != cudaSuccess) { cudaFree(p); return nullptr; }
+    return p;
+}
 
 struct wspr_ctx {
     int device = 0, maxcap = 0, np = 0, stride = 0, blocks = 0;
     int ncap = 0;
+    FanoService *svc = nullptr;
     cudaStream_t st = nullptr;
+    cudaStream_t fano_st[NFANO_STREAMS] = {nullptr};   // worker warps are launched here (the pool's SM partition, if any)
+    int fano_rr = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_wait = nullptr;   // blocking-sync event: host threads sleep instead of spinning while the GPU works
+    cudaEvent_t ev_fano = nullptr;   // the round's candidates are in the queue
     float *I = nullptr, *Q = nullptr, *psT = nullptr, *smspec = nullptr;
     Cand *cands = nullptr;
     CapState *caps = nullptr;
@@ -91,16 +218,20 @@ struct wspr_ctx {
     int *nres = nullptr;
     Job *jobs = nullptr;           // [maxcap] the candidate each capture is working on
     Attempt *att0 = nullptr;       // [maxcap] its jitter-0 attempt
-    int *ident = nullptr, *setup_list = nullptr, *job_list = nullptr, *res_list = nullptr, *sub_list = nullptr;
+    int *ident = nullptr, *setup_list = nullptr, *job_list = nullptr, *res_list = nullptr, *sub_list = nullptr, *defer_list = nullptr;
     float4 *P0 = nullptr, *P1 = nullptr, *tabs = nullptr;
     float *phi0 = nullptr;
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
     Counters *h_cnt = nullptr;     // pinned host mirror
+    ChainScratch *scratch = nullptr;   // [maxcap], leased from the service
+    int *h_done = nullptr;         // pinned, device-visible: parked captures handed back by the Fano workers so far
     char *preload = nullptr;       // device [32768][13]: hashtable.txt calls (allocated on the first -H decode)
     int *stats = nullptr;          // device [8]: how deferred candidates were settled
     int h_stats[8] = {0};
-    SideSlot side[NSIDE];
+    unsigned fano_budget = 4096;   // WSPR_FANO_BUDGET (read when the context is created)
+    int park_linger_us = 300;      // WSPR_PARK_LINGER_US: how long to wait for more parked captures once one has come back
+    bool trace = false;            // WSPR_TRACE
     float last_ms = 0.0f, sync_ms = 0.0f;
     int sync_launches = 0, rounds = 0, deferred = 0;
     double sync_cells = 0.0;
@@ -117,21 +248,23 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
-                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->P0, c->P1, c->tabs, c->phi0, c->ref, c->cprod, c->cnt, c->stats, c->preload};
+                    c->setup_list, c->job_list, c->res_list, c->sub_list, c->defer_list, c->P0, c->P1, c->tabs, c->phi0, c->ref, c->cprod,
+                    c->cnt, c->stats, c->preload};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    for (SideSlot &s : c->side) {
-        void *sp[] = {s.list, s.count, s.scratch, s.list2, s.count2};
-        for (void *p : sp)
-            if (p) cudaFree(p);
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.st) cudaStreamDestroy(s.st);
+    if (c->scratch && c->svc) {
+        std::lock_guard<std::mutex> lock(c->svc->mu);
+        c->svc->free_scratch.push_back({(size_t)c->maxcap, c->scratch});
     }
+    for (cudaStream_t s : c->fano_st)
+        if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+    if (c->ev_fano) cudaEventDestroy(c->ev_fano);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -148,12 +281,17 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     c->np = samples;
     c->stride = (samples + 127) / 128 * 128;
     c->blocks = 4 * (samples / NFFT) - 1;                    // wsprd.c:516
-    // (Stream priorities were tried -- main stream highest, side streams lowest, so that pending bulk blocks are dispatched
-    // ahead of pending chain blocks: 2 % slower end to end, and a background Fano grid still serialises a decode behind it.)
-    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    c->svc = fano_service(device);
+    if (!c->svc) return fail(WSPR_ERR_CUDA, "Fano service set-up failed", cudaGetLastError());
+    CK(service_stream(c->svc, false, &c->st));
+    for (cudaStream_t &s : c->fano_st) CK(service_stream(c->svc, true, &s));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_fano, cudaEventDisableTiming));
+    c->fano_budget = (unsigned)std::max(256, env_int("WSPR_FANO_BUDGET", 4096));   // tuning knob, read once
+    c->trace = getenv("WSPR_TRACE") != nullptr;
+    c->park_linger_us = env_int("WSPR_PARK_LINGER_US", 300);
     size_t B = (size_t)maxcap;
     CK(dalloc(&c->I, B * c->stride));
     CK(dalloc(&c->Q, B * c->stride));
@@ -173,6 +311,7 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     CK(dalloc(&c->job_list, B));
     CK(dalloc(&c->res_list, B));
     CK(dalloc(&c->sub_list, B));
+    CK(dalloc(&c->defer_list, B));
     CK(dalloc(&c->P0, B * MAXLAGS * NSYM));
     CK(dalloc(&c->P1, B * NFREQ1 * NSYM));
     CK(dalloc(&c->tabs, B * NFREQ1 * 2 * SPS));
@@ -187,16 +326,10 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
         for (size_t i = 0; i < B; i++) id[i] = (int)i;
         CK(cudaMemcpy(c->ident, id.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     }
-    for (SideSlot &s : c->side) {
-        CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming));
-        CK(dalloc(&s.list, B));
-        CK(dalloc(&s.count, 1));
-        s.chain_cap = std::max(8, std::min(maxcap, 1024));
-        CK(dalloc(&s.scratch, (size_t)s.chain_cap));
-        CK(dalloc(&s.list2, (size_t)s.chain_cap));
-        CK(dalloc(&s.count2, 1));
-    }
+    c->scratch = lease_scratch(c->svc, B);
+    if (!c->scratch) return fail(WSPR_ERR_CUDA, "ChainScratch allocation", cudaGetLastError());
+    CK(cudaMallocHost((void **)&c->h_done, sizeof(int)));
+    *c->h_done = 0;
     HostTables t;
     host_tables(t);
     upload_tables(t);
@@ -264,8 +397,7 @@ static DecodeParams make_params(const wspr_ctx *c, const decoder_options &o) {
     p.lagstep = o.quickmode ? 16 : 8;                        // wsprd.c:715-717
     p.nlags = 256 / p.lagstep + 1;
     p.preload = nullptr;
-    p.fano_budget = 4096;
-    if (const char *e = getenv("WSPR_FANO_BUDGET")) p.fano_budget = (unsigned)std::max(256, atoi(e));   // tuning knob
+    p.fano_budget = c->fano_budget;
     return p;
 }
 
@@ -297,29 +429,30 @@ static int read_counters(wspr_ctx *c) {
     return wait_stream(c);
 }
 
-// a side slot whose previous work has completed (waits for the oldest one if all are in flight)
-static int acquire_side(wspr_ctx *c, SideSlot **out) {
-    for (int pass = 0; pass < 2; pass++) {
-        for (SideSlot &s : c->side) {
-            if (s.busy && cudaEventQuery(s.done) == cudaSuccess) s.busy = false;
-            if (!s.busy) {
-                *out = &s;
-                return WSPR_OK;
-            }
+// every open capture is parked with the Fano workers: sleep until one more has been handed back (`seen`: the count
+// read before the round was planned, so a hand-back in between is not missed)
+// `want` more hand-backs are worth waiting a little longer for (a round costs two host synchronisations whatever its size)
+static int wait_parked(wspr_ctx *c, int seen, int want) {
+    const volatile int *done = c->h_done;
+    for (unsigned spin = 0; *done == seen; spin++) {
+        if ((spin & 1023u) == 1023u) {             // (a failed kernel would otherwise leave us here for good)
+            cudaError_t e = cudaStreamQuery(c->fano_st[0]);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(WSPR_ERR_CUDA, "Fano workers", e);
         }
-        if (wait_event(c->side[0].done)) return WSPR_ERR_CUDA;
+        if (wait_blocks()) usleep(50);
+        else sched_yield();
     }
-    return fail(WSPR_ERR_CUDA, "no side stream available");
-}
-
-static int wait_any_side(wspr_ctx *c) {
-    for (SideSlot &s : c->side)
-        if (s.busy) {
-            if (wait_event(s.done)) return WSPR_ERR_CUDA;
-            s.busy = false;
-            return WSPR_OK;
+    if (c->park_linger_us > 0 && want > 1) {
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        while (*done - seen < want) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if ((t1.tv_sec - t0.tv_sec) * 1000000L + (t1.tv_nsec - t0.tv_nsec) / 1000L >= c->park_linger_us) break;
+            if (wait_blocks()) usleep(50);
+            else sched_yield();
         }
-    return fail(WSPR_ERR_CUDA, "scheduler stalled: captures parked but no side stream is in flight");
+    }
+    return WSPR_OK;
 }
 
 // ---- options.usehashtable (reference -H): hashtable.txt in the CWD, wsprd.c:481-494 and :842-852 ----
@@ -396,11 +529,12 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     c->deferred = 0;
     c->kev_jobs.clear();
     size_t kev_used = 0;
-    const bool trace = getenv("WSPR_TRACE") != nullptr;
+    const bool trace = c->trace;
     CK(cudaEventRecord(c->ev0, c->st));
     CK(cudaMemsetAsync(c->stats, 0, 8 * sizeof(int), c->st));
     launch_reset_caps(c->caps, ncap, o.npasses, c->st);
     while (ncap > 0) {
+        const int seen = *(volatile int *)c->h_done;
         launch_plan(c->caps, c->cands, c->jobs, c->setup_list, c->job_list, c->res_list, c->cnt, ncap, o.npasses, c->st);
         if (read_counters(c)) return WSPR_ERR_CUDA;
         const Counters h = *c->h_cnt;
@@ -413,8 +547,8 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                     h.nsetup, h.njobs, h.nres, h.nwait, h.ndone);
         }
         if (h.ndone == ncap) break;
-        if (h.nsetup == 0 && h.njobs == 0 && h.nres == 0) {   // everything still open is parked on a side stream
-            if (wait_any_side(c)) return WSPR_ERR_CUDA;
+        if (h.nsetup == 0 && h.njobs == 0 && h.nres == 0) {   // everything still open is parked with the Fano workers
+            if (wait_parked(c, seen, std::min(h.nwait, 64))) return WSPR_ERR_CUDA;
             continue;
         }
         c->rounds++;
@@ -425,9 +559,6 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
         // one candidate of every ready capture (wsprd.c:697-766)
         int nres_max = h.nres;
         if (h.njobs > 0) {
-            SideSlot *side = nullptr;
-            if (acquire_side(c, &side)) return WSPR_ERR_CUDA;
-            CK(cudaMemsetAsync(side->count, 0, sizeof(int), c->st));
             if (c->time_kernels) {
                 while (c->kev.size() < kev_used + 2) {
                     cudaEvent_t e;
@@ -444,18 +575,19 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             }
             launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->P1, c->tabs, c->att0, p, c->st);
             launch_fano_round(c->att0, c->job_list, h.njobs, p, c->st);
-            launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, side->list, side->count, c->cnt, p,
-                           c->st);
+            launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, c->defer_list, c->cnt, p, c->st);
             if (read_counters(c)) return WSPR_ERR_CUDA;
             const int ndefer = c->h_cnt->ndefer;
             nres_max = c->h_cnt->nres;
             if (ndefer > 0) {                                 // finish them off the critical path
                 c->deferred += ndefer;
-                for (int off = 0; off < ndefer; off += side->chain_cap)   // (more than chain_cap parked at once: in turn)
-                    launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, side->list + off, std::min(side->chain_cap, ndefer - off),
-                                    side->scratch, side->list2, side->count2, c->stats, p, side->st);
-                CK(cudaEventRecord(side->done, side->st));
-                side->busy = true;
+                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer, c->scratch, c->stats, c->h_done,
+                                c->svc->queue, p, c->st);
+                CK(cudaEventRecord(c->ev_fano, c->st));
+                cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];
+                CK(cudaStreamWaitEvent(fs, c->ev_fano, 0));
+                const int attempts = ndefer * (p.quickmode ? 1 : NJIT);
+                launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), p, fs);
             }
         }
         // in-order tail of the candidate loop for everything that finished, then the subtractions (wsprd.c:768-822)
@@ -469,6 +601,11 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     CK(cudaEventRecord(c->ev1, c->st));
     if (wait_stream(c)) return WSPR_ERR_CUDA;
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    {
+        int overflow = 0;
+        CK(cudaMemcpy(&overflow, &c->svc->queue->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+        if (overflow) return fail(WSPR_ERR_CUDA, "Fano queue overflow: parked candidates were lost");
+    }
     if (ht) {
         if (hashtable_merge(c, *ht)) return WSPR_ERR_CUDA;
         hashtable_write(*ht);
@@ -496,6 +633,30 @@ extern "C" int wspr_ctx_last_stats(wspr_ctx *c, int *out8) {
     for (int i = 0; i < 8; i++) out8[i] = c->h_stats[i];
     return WSPR_OK;
 }
+// Fano worker pool of `device` (-1: the current one): out[0] worker warps allowed, [1] SMs set aside for them (0: shared),
+// [2] housekeeping periods (256 loop trips) the worker warps were alive for, [3] lane-periods with an attempt in the lane
+// (utilisation = [3] / (32 [2])), [4] attempts decoded to their end, [5] attempts skipped or abandoned, [6] worker warps
+// started; reset != 0 clears the counters.  Returns 0, or a negative error when no context exists on the device yet.
+extern "C" int wspr_fano_stats(int device, unsigned long long *out8, int reset) {
+    if (!out8) return fail(WSPR_ERR_ARG, "wspr_fano_stats");
+    if (device < 0) CK(cudaGetDevice(&device));
+    FanoService *s = (device >= 0 && device < 64) ? g_svc[device] : nullptr;
+    if (!s) return fail(WSPR_ERR_ARG, "wspr_fano_stats: no context on this device yet");
+    CK(cudaSetDevice(device));
+    FanoQueue h;
+    CK(cudaMemcpy(&h, s->queue, sizeof h, cudaMemcpyDeviceToHost));
+    out8[0] = (unsigned long long)s->pool;
+    out8[1] = (unsigned long long)s->fano_sms;
+    out8[2] = h.st_warp_periods;
+    out8[3] = h.st_lane_periods;
+    out8[4] = h.st_attempts;
+    out8[5] = h.st_dropped;
+    out8[6] = h.st_warps;
+    out8[7] = 0;
+    if (reset) CK(cudaMemset(&s->queue->st_warp_periods, 0, 5 * sizeof(unsigned long long)));
+    return WSPR_OK;
+}
+
 extern "C" int wspr_ctx_time_kernels(wspr_ctx *c, int on) {
     if (!c) return WSPR_ERR_ARG;
     c->time_kernels = on != 0;
@@ -625,7 +786,8 @@ extern "C" int wspr_decode(float *idat, float *qdat, int samples, decoder_option
 }
 
 // Fano decoder kernel on caller-supplied soft symbols (n vectors of 162 deinterleaved bytes): the device counterpart
-// of fano() (wsprd/fano.h:14-28) for batches.  solo != 0 selects the one-attempt-per-warp form used for long runs.
+// of fano() (wsprd/fano.h:14-28) for batches.  solo & 1: one attempt per warp (the latency of a lone attempt); solo & 4: the
+// instantiation the decode kernels run (time-out test every 256 trips, maxnp not tracked) instead of the exact one.
 // Outputs are host arrays of n entries (data: n x 12 bytes); returns 0 or a negative error.
 extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo,
                                int *rc, unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data,
@@ -636,7 +798,6 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     int *d_rc = nullptr;
     unsigned *d_m = nullptr, *d_c = nullptr, *d_x = nullptr;
     unsigned long long *d_k = nullptr;
-    unsigned char *d_g = nullptr;                          // (solo & 2): tree state in global memory instead of shared
     int ret = WSPR_OK;
     cudaError_t e = cudaMalloc((void **)&d_sym, (size_t)n * NSYM);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_data, (size_t)n * 12);
@@ -644,11 +805,10 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_m, (size_t)n * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_c, (size_t)n * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_x, (size_t)n * sizeof(unsigned));
-    if (e == cudaSuccess && (solo & 2)) e = cudaMalloc((void **)&d_g, (size_t)((solo & 1) ? n : (n + 31) / 32) * fano_warp_scratch_bytes());
     if (e == cudaSuccess && clocks) e = cudaMalloc((void **)&d_k, (size_t)n * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpy(d_sym, symbols, (size_t)n * NSYM, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        launch_fano_test(d_sym, n, delta, maxcycles, stop_after, solo, d_rc, d_m, d_c, d_x, d_data, d_k, d_g, 0);
+        launch_fano_test(d_sym, n, delta, maxcycles, stop_after, solo, d_rc, d_m, d_c, d_x, d_data, d_k, 0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(rc, d_rc, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
@@ -658,63 +818,8 @@ extern "C" int wspr_fano_batch(const unsigned char *symbols, int n, int delta, u
     if (e == cudaSuccess) e = cudaMemcpy(data, d_data, (size_t)n * 12, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && clocks) e = cudaMemcpy(clocks, d_k, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) ret = fail(WSPR_ERR_CUDA, "wspr_fano_batch", e);
-    cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k); cudaFree(d_g);
+    cudaFree(d_sym); cudaFree(d_data); cudaFree(d_rc); cudaFree(d_m); cudaFree(d_c); cudaFree(d_x); cudaFree(d_k);
     return ret;
-}
-
-// Experiment hook (tools/exp_interference.py): put `nctas` one-warp CTAs in flight on a private stream and return at once;
-// wspr_debug_fano_load(0, 0, 0) waits for them.  mode 0: Fano on hopeless attempts, tree state in shared memory (the shape of
-// k_chain_fano); 2: the same with the tree state in global memory (no shared memory held); 8: CTAs that hold 84 KB of
-// shared memory and sleep; 9: sleep without shared memory; 10: a dependent integer loop at ~1 instruction per 4 clocks
-// without shared memory.  Not part of the product path.
-__global__ void k_debug_resident(int mode, long long clocks, unsigned *sink) {
-    extern __shared__ unsigned dbg_smem[];
-    const long long t0 = clock64();
-    unsigned x = threadIdx.x;
-    if (mode == 10) {
-        while (clock64() - t0 < clocks) {
-#pragma unroll
-            for (int k = 0; k < 64; k++) x = x * 1664525u + 1013904223u;
-        }
-    } else {
-        while (clock64() - t0 < clocks) __nanosleep(2000);
-    }
-    if (x == 0xdeadbeefu) sink[0] = x + (mode == 8 ? dbg_smem[threadIdx.x] : 0u);
-}
-extern "C" int wspr_debug_fano_load(int nctas, unsigned maxcycles, int mode) {
-    static cudaStream_t st = nullptr;
-    static unsigned char *d_sym = nullptr, *d_g = nullptr;
-    static int *d_i = nullptr;
-    static unsigned *d_u = nullptr;
-    static unsigned char *d_data = nullptr;
-    const int cap = 1024 * 32;
-    if (!st) {
-        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        CK(cudaMalloc((void **)&d_sym, (size_t)cap * NSYM));
-        CK(cudaMalloc((void **)&d_i, (size_t)cap * sizeof(int)));
-        CK(cudaMalloc((void **)&d_u, (size_t)3 * cap * sizeof(unsigned)));
-        CK(cudaMalloc((void **)&d_data, (size_t)cap * 12));
-        CK(cudaMalloc((void **)&d_g, (size_t)1024 * fano_warp_scratch_bytes()));
-        std::vector<unsigned char> h((size_t)cap * NSYM);
-        unsigned x = 12345u;
-        for (auto &b : h) { x = x * 1664525u + 1013904223u; b = (unsigned char)(x >> 24); }
-        CK(cudaMemcpy(d_sym, h.data(), h.size(), cudaMemcpyHostToDevice));
-        CK(cudaFuncSetAttribute(k_debug_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, 84480));
-    }
-    if (nctas <= 0) {
-        CK(cudaStreamSynchronize(st));
-        return WSPR_OK;
-    }
-    nctas = std::min(nctas, 1024);
-    if (mode >= 8) {
-        // maxcycles x 81 Fano cycles at ~290 clocks each, so that the load lasts as long as the Fano loads do
-        k_debug_resident<<<nctas, 32, mode == 8 ? 84480 : 0, st>>>(mode, (long long)maxcycles * 81 * 290, d_u);
-    } else {
-        launch_fano_test(d_sym, nctas * 32, 60, maxcycles, 0, mode & 2, d_i, d_u, d_u + cap, d_u + 2 * cap, d_data, nullptr,
-                         (mode & 2) ? d_g : nullptr, st);
-    }
-    CK(cudaGetLastError());
-    return WSPR_OK;
 }
 
 // sync_and_demodulate: correlation grid on the GPU, the handful of scalar reductions on the host in the

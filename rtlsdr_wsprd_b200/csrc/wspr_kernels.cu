@@ -20,7 +20,6 @@ static std::atomic<unsigned long long> g_launches{0};   // contexts may be drive
 extern unsigned long long g_frontend_launches;   // wspr_frontend.cu
 unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend_launches; }
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
-static void fano_attrs();                                  // one-time kernel attributes (end of this file)
 
 // ---- constant tables ----------------------------------------------------------------------------------
 __device__ float c_window_g[NFFT];    // (indexed in bit-reversed order by the lanes: global/L1, not the constant bank)
@@ -31,9 +30,7 @@ __constant__ float c_floor_snr;
 __constant__ short c_mettab[2][256] = WSPR_METTAB_INIT;
 __device__ const double g_tw[256][2] = FFT512_TWIDDLE_INIT;
 
-void init_kernel_attributes();
 void upload_tables(const HostTables &t) {
-    init_kernel_attributes();
     cudaMemcpyToSymbol(c_window_g, t.window, sizeof t.window);
     cudaMemcpyToSymbol(c_lpf_w, t.lpf_w, sizeof t.lpf_w);
     cudaMemcpyToSymbol(c_lpf_psum, t.lpf_psum, sizeof t.lpf_psum);
@@ -927,7 +924,6 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
     LAUNCHED();
     k_sync_freqs<<<dim3(njobs, NFREQ1), 192, 0, st>>>(I, Q, jobs, job_list, P0, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
-    fano_attrs();                                             // (also opts k_sync_freqs_shared in to its dynamic shared memory)
     k_sync_freqs_shared<<<njobs, SF_THREADS, SF_SMEM_BYTES, st>>>(I, Q, jobs, job_list, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
@@ -936,48 +932,20 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
 
 // =========================================================================================================
 // K5  Fano decoder (fano.c:87-238), metric table in constant memory, lane-dense branch-free form (wspr_fano.cuh).
-//   k_fano_round  jitter-0 attempts of a round, 32 attempts per warp, at most fano_budget cycles each: nearly every
-//                 decodable candidate finishes within a few hundred cycles; the rest is finished on a side stream
-//   k_chain_fano  all 43 attempts of one parked candidate in one CTA (below)
+//   k_fano_round    jitter-0 attempts of a round, 32 attempts per warp, at most fano_budget cycles each: nearly every
+//                   decodable candidate finishes within a few hundred cycles; the rest is parked
+//   k_fano_workers  the pool of worker warps that serves the device-wide queue of parked attempts (below)
 // =========================================================================================================
-struct ChainStop {                                             // abandon an attempt once a lower-numbered one decoded
-    int *best;
-    int idt;
-    __device__ bool stop() const { return *(const volatile int *)best < idt; }
-    template <typename Mem>
-    __device__ void success(unsigned, const Mem &, unsigned) const { atomicMin(best, idt); }
-};
-// jitter-0 attempt of a parked candidate, one candidate per lane (k_chain_first): a decode hands the capture back to the
-// rounds at once, without waiting for the other 31 candidates of the warp
-struct FirstHook {
-    Job *job;
-    CapState *cs;
-    int *stats;
-    __device__ bool stop() const { return false; }
-    template <typename Mem>
-    __device__ void success(unsigned cycles, const Mem &mem, unsigned node_base) const {
-        for (int b = 0; b < 12; b++) job->dec[b] = 0;
-        for (int b = 0; b < (NBITS >> 3); b++) job->dec[b] = (unsigned char)mem.ld(node_base + mem.row * (unsigned)(7 + 8 * b)).x;
-        job->cycles = cycles;
-        job->decoded = 1;
-        job->idt = 0;
-        atomicAdd(stats + 0, 1);
-        __threadfence();
-        *(volatile int *)&cs->phase = PH_RESOLVE;
-    }
-};
-static void fano_attrs();
-
 __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, const int *__restrict__ job_list, int njobs,
                                                    int delta, unsigned maxcycles, unsigned budget) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
     const int i = blockIdx.x * 32 + threadIdx.x;
     Attempt *a = (i < njobs) ? &att0[job_list[i]] : nullptr;
     const bool want = a != nullptr && a->gate;
-    FanoResult r;
-    fano_dense<false>(r, want, want ? a->sym : nullptr, &c_mettab[0][0], delta, maxcycles, budget, FanoNoStop(),
-               FanoSmem::at(fano_smem, 512u));
+    FanoOneShot feed{want ? a->sym : nullptr, budget, {}};
+    fano_run<false>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);
     if (want) {
+        const FanoResult &r = feed.res;
         a->ok = (r.rc == 0);
         a->unfinished = (r.rc == FANO_STOPPED);
         a->cycles = r.cycles;
@@ -987,17 +955,16 @@ __global__ void __launch_bounds__(32) k_fano_round(Attempt *__restrict__ att0, c
 
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    fano_attrs();
     k_fano_round<<<(njobs + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(att0, job_list, njobs, p.delta, p.maxcycles, p.fano_budget);
     LAUNCHED();
 }
 
 // triage after the jitter-0 attempt: finished candidates go to this round's resolve list; candidates that are worth
 // a try but still undecided (unfinished Fano run, or not decoded and the jitter search is still to come, :741-766)
-// are parked and handed to a side stream.
+// are parked and handed to the Fano workers.
 __global__ void k_collect(Job *__restrict__ jobs, const Attempt *__restrict__ att0, CapState *__restrict__ caps,
                           const int *__restrict__ job_list, int njobs, int *__restrict__ res_list,
-                          int *__restrict__ defer_list, int *__restrict__ defer_count, Counters *cnt, int quickmode) {
+                          int *__restrict__ defer_list, Counters *cnt, int quickmode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= njobs) return;
     const int cap = job_list[i];
@@ -1014,51 +981,61 @@ __global__ void k_collect(Job *__restrict__ jobs, const Attempt *__restrict__ at
     }
     if (defer) {
         caps[cap].phase = PH_WAIT;
-        defer_list[atomicAdd(defer_count, 1)] = cap;
-        atomicAdd(&cnt->ndefer, 1);
+        defer_list[atomicAdd(&cnt->ndefer, 1)] = cap;
     } else {
         res_list[atomicAdd(&cnt->nres, 1)] = cap;
     }
 }
 
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
-                    int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st) {
+                    int *defer_list, Counters *cnt, const DecodeParams &p, cudaStream_t st) {
     if (njobs <= 0) return;
-    k_collect<<<(njobs + 127) / 128, 128, 0, st>>>(jobs, att0, caps, job_list, njobs, res_list, defer_list, defer_count, cnt,
-                                                   p.quickmode);
+    k_collect<<<(njobs + 127) / 128, 128, 0, st>>>(jobs, att0, caps, job_list, njobs, res_list, defer_list, cnt, p.quickmode);
     LAUNCHED();
 }
 
-// ---- deferred candidates (side stream) --------------------------------------------------------------------------
-// What is left of a parked candidate's jitter loop (wsprd.c:741-766) runs with every attempt in flight at once --
-// attempt 0 is the unfinished jitter-0 Fano run (now with the reference's full cycle budget), attempts 1..42 are the
-// jittered ones, shift + 3*(+-1..21):
-//   k_jitter_soft  grid (candidate, jitter): the jittered soft-symbol vectors and their gates (mode 2 of
-//                  sync_and_demodulate + the rms test), written to the candidate's scratch record;
-//   k_chain_fano   one 64-thread CTA per candidate, one lane per attempt, lane-dense Fano; an attempt is abandoned as
-//                  soon as a lower-numbered one has succeeded -- the reference's sequential loop would never have
-//                  reached it.  Winner = lowest successful attempt, exactly what the sequential loop returns; the CTA
-//                  then hands the capture back to the rounds.  No barrier with other parked candidates anywhere.
-// stats: [0] settled by the full-budget jitter-0 run, [1] by a jittered attempt, [2] never decoded
+// ---- parked candidates -------------------------------------------------------------------------------------------
+// What is left of a parked candidate's jitter loop (wsprd.c:741-766): attempt 0 is the unfinished jitter-0 Fano run (now
+// with the reference's full cycle budget), attempts 1..42 are the jittered ones, shift + 3*(+-1..21).
+//   k_jitter_soft   grid (candidate, jitter): the jittered soft-symbol vectors and their gates (mode 2 of
+//                   sync_and_demodulate + the rms test), written to the capture's scratch record;
+//   k_fano_enqueue  the round's candidates go into the device-wide queue (wspr_kernels.cuh, FanoQueue);
+//   k_fano_workers  a pool of one-warp CTAs, every LANE of which takes an attempt, decodes it, publishes the result and
+//                   takes the next one (the lanes of a warp work on unrelated attempts; wspr_fano.cuh).  Attempt 0 of every
+//                   queued candidate is handed out before any jittered attempt -- what the reference would run first is
+//                   served first.  An attempt is skipped or abandoned as soon as a lower-numbered attempt of its candidate
+//                   has decoded (the reference's sequential loop would never have reached it), and the lane that decodes
+//                   retires the candidate's unclaimed attempts itself.  Winner = lowest successful attempt, exactly what
+//                   the sequential loop returns; the lane that accounts for a candidate's last attempt writes the outcome
+//                   into the job and hands the capture back to the rounds.
+// Round 1 gave every parked candidate its own 1.5 warps for as long as its slowest attempt ran (~1 200 one-warp CTAs of
+// 84 KB per 4096-capture batch, a third of the lanes idle, jittered attempts started whether or not attempt 0 was about to
+// succeed); the pool keeps its lanes full, runs attempt 0 first and is a fixed, small number of warps.
 __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
-                                                     const Job *__restrict__ jobs, const Attempt *__restrict__ att0,
-                                                     const int *__restrict__ defer_list, const int *__restrict__ count,
-                                                     int skip0, ChainScratch *__restrict__ scratch, int np, int stride,
+                                                     Job *__restrict__ jobs, const Attempt *__restrict__ att0,
+                                                     CapState *__restrict__ caps, const int *__restrict__ defer_list,
+                                                     ChainScratch *__restrict__ scratch, int *__restrict__ stats,
+                                                     int *__restrict__ host_done, int nattempts, int np, int stride,
                                                      float minrms, int symfac, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float4 P[NSYM];
     const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
-    if (count && e >= *count) return;                          // (list filled on the device: the grid is sized for the worst case)
     const int cap = defer_list[e];
     const Job &job = jobs[cap];
-    ChainScratch &cs = scratch[e];
+    ChainScratch &cs = scratch[cap];
     if (idt == 0) {                                            // attempt 0: the parked jitter-0 soft symbols
         const Attempt &a = att0[cap];
         for (int i = t; i < NSYM; i += 192) cs.sym[0][i] = a.sym[i];
         if (t == 0) {
-            cs.gate[0] = !skip0 && a.gate && a.unfinished;   // (skip0: the jitter-0 attempt has already been run to the end)
+            cs.gate[0] = a.gate && a.unfinished;             // (else it already ran to its end inside the round, or is gated off)
+            cs.ok[0] = cs.unfinished[0] = 0;
             cs.best = NJIT;                                    // no attempt has decoded yet
             cs.done = 0;
+            cs.nattempts = nattempts;
+            cs.job = &jobs[cap];
+            cs.phase = &caps[cap].phase;
+            cs.stats = stats;
+            cs.host_done = host_done;
         }
         return;
     }
@@ -1078,179 +1055,211 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
         float rms;
         const float s2 = soft_symbols(P, cs.sym[idt], &rms, symfac);
         cs.gate[idt] = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
+        cs.ok[idt] = cs.unfinished[idt] = 0;
     }
 }
 
-// One-warp pieces.  Piece e < n runs attempts 0..31 of candidate e; piece n + j runs the remaining attempts 32..42 of
-// candidates 2j (lanes 0..10) and 2j+1 (lanes 16..26).  The piece that finishes last picks the winner and hands the capture
-// back.  A CTA carries CHAIN_PIECES pieces, one warp each, completely independent of each other (no CTA barrier).
-// One piece per CTA by default.  Two were tried (WSPR_CHAIN_PIECES=2), on the theory that what a resident Fano warp costs
-// the bulk kernels is per SM rather than per warp, so parked work should sit on half as many SMs: 9 % slower end to end
-// -- a 170 KB CTA has to wait for a nearly empty SM and then excludes everything else from it.
-constexpr int CHAIN_PIECES = 2;
-// PIPE: the pipelined form of the decoder loop (wspr_fano.cuh), selected with WSPR_FANO_PIPE=1 -- checked against the oracle
-// on the host (tests/test_fano_host.py) and through wspr_fano_batch on the GPU, not yet the default.
-template <bool PIPE>
-__global__ void __launch_bounds__(32 * CHAIN_PIECES) k_chain_fano(Job *__restrict__ jobs, CapState *__restrict__ caps,
-                                                                 const int *__restrict__ defer_list,
-                                                                 ChainScratch *__restrict__ scratch, int n, int npieces,
-                                                                 const int *__restrict__ count, int nattempts, int delta,
-                                                                 unsigned maxcycles, int *__restrict__ stats) {
-    extern __shared__ __align__(16) unsigned char fano_smem_all[];
-    if (count) {                                               // list filled on the device: the grid is sized for the worst case
-        n = *count;
-        npieces = n + (nattempts > 32 ? (n + 1) / 2 : 0);
+__global__ void __launch_bounds__(256) k_fano_enqueue(FanoQueue *__restrict__ q, ChainScratch *__restrict__ scratch,
+                                                      const int *__restrict__ defer_list, int n) {
+    __shared__ unsigned s_base;
+    if (threadIdx.x == 0) {
+        const unsigned base = atomicAdd(&q->tail, (unsigned)n);
+        const unsigned h0 = *(volatile unsigned *)&q->head0, h1 = *(volatile unsigned *)&q->head1;
+        const unsigned oldest = (int)(h0 - h1) < 0 ? h0 : h1;
+        if (base + (unsigned)n - oldest > q->mask + 1u) q->overflow = 1;   // (then entries are overwritten: the host reports it)
+        s_base = base;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int piece = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
-    if (piece >= npieces) return;
-    unsigned char *fano_smem = fano_smem_all + (size_t)warp * FANO_WARP_SMEM_BYTES;
-    int e, idt;
-    if (piece < n) {
-        e = piece;
-        idt = lane;
-    } else {
-        e = 2 * (piece - n) + (lane >> 4);
-        idt = 32 + (lane & 15);
-    }
-    const bool mine = e < n && idt < nattempts;
-    ChainScratch &cs = scratch[mine ? e : 0];
-    const bool want = mine && cs.gate[idt];
-    FanoResult r;
-    ChainStop stop{&cs.best, idt};
-    fano_dense<false, PIPE>(r, want, cs.sym[mine ? idt : 0], &c_mettab[0][0], delta, maxcycles, 0, stop,
-                            FanoSmem::at(fano_smem, 512u));
-    if (mine) {
-        cs.ok[idt] = want && (r.rc == 0);
-        cs.unfinished[idt] = want && (r.rc == FANO_STOPPED);
-        cs.cycles[idt] = r.cycles;
-        for (int k = 0; k < 12; k++) cs.dec[idt][k] = r.data[k];
-    }
-    __syncwarp();
-    if (e < n && (lane & 15) == 0 && (piece >= n || lane == 0)) {   // one arrival per (piece, candidate)
-        const int pieces = nattempts > 32 ? 2 : 1;
+    __syncthreads();
+    const unsigned base = s_base;
+    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+        ChainScratch *cs = scratch + defer_list[i];
+        *(volatile int *)&cs->next = 1;                        // (everything k_jitter_soft wrote is complete: previous kernel)
+        FanoQueueEntry &x = q->ring[(base + i) & q->mask];
+        *(ChainScratch *volatile *)&x.cs = cs;
         __threadfence();
-        const int arrived = atomicAdd(&cs.done, 1);
-        if (arrived == pieces - 1) {                           // the other piece's results are complete and visible
-            __threadfence();
-            const int cap = defer_list[e];
-            Job &job = jobs[cap];
-            const volatile ChainScratch &v = cs;
-            for (int y = 0; y < nattempts; y++) {
-                if (v.gate[y] && !v.unfinished[y]) job.cycles = v.cycles[y];
-                if (v.gate[y] && v.ok[y]) {
-                    job.decoded = 1;
-                    job.idt = y;
-                    for (int k = 0; k < 12; k++) job.dec[k] = v.dec[y][k];
-                    break;
-                }
-            }
-            atomicAdd(stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
-            __threadfence();
-            *(volatile int *)&caps[cap].phase = PH_RESOLVE;
+        *(volatile unsigned *)&x.seq = base + i + 1u;
+    }
+}
+
+// `count` attempts of the capture's parked candidate are accounted for; the lane that accounts for the last one leaves the
+// outcome in the job and hands the capture back
+__device__ void fano_settle(ChainScratch *cs, int count) {
+    __threadfence();
+    const int arrived = atomicAdd(&cs->done, count);
+    const int na = *(volatile int *)&cs->nattempts;
+    if (arrived + count != na) return;
+    __threadfence();                                           // the other attempts' results are complete and visible
+    Job &job = *cs->job;
+    const volatile ChainScratch &v = *cs;
+    for (int y = 0; y < na; y++) {
+        if (v.gate[y] && !v.unfinished[y]) job.cycles = v.cycles[y];
+        if (v.gate[y] && v.ok[y]) {
+            job.decoded = 1;
+            job.idt = y;
+            for (int k = 0; k < 12; k++) job.dec[k] = v.dec[y][k];
+            break;
         }
     }
+    atomicAdd(cs->stats + (job.decoded ? (job.idt == 0 ? 0 : 1) : 2), 1);
+    __threadfence();
+    *(volatile int *)cs->phase = PH_RESOLVE;
+    __threadfence_system();
+    atomicAdd_system(cs->host_done, 1);                        // (mapped host memory: wakes a host thread with nothing else to do)
 }
 
-// Two-stage form of the parked candidates (WSPR_CHAIN_STAGES=2, off by default).  Stage 1: the jitter-0 attempts with the
-// full budget, ONE CANDIDATE PER LANE (32 per warp).  Most parked candidates (78 % on the config-3 corpus) decode here,
-// after 4 096 .. 810 000 cycles; the single-stage form gives each of them its own 1.5 warps for all 43 attempts, i.e.
-// ~1 200 one-warp CTAs per batch resident for as long as their jitter-0 run takes.  A candidate that decodes is handed
-// back at once (FirstHook); the others are appended to list2 for stage 2 (the 42 jittered attempts, k_jitter_soft +
-// k_chain_fano with attempt 0 masked), or, in quick mode, handed back undecoded.
-// Measured: results identical (GPU suite green with it), 4 % SLOWER end to end -- a candidate that needs the jitter
-// search now waits for the slowest jitter-0 attempt of its whole round before its 42 attempts even start (88 rounds per
-// batch instead of 66), and that latency costs more than the shorter residence gains.
-__global__ void __launch_bounds__(32) k_chain_first(Job *__restrict__ jobs, CapState *__restrict__ caps,
-                                                    const Attempt *__restrict__ att0, const int *__restrict__ defer_list, int n,
-                                                    int delta, unsigned maxcycles, int quick, int *__restrict__ list2,
-                                                    int *__restrict__ count2, int *__restrict__ stats) {
+struct FanoQueueFeed {
+    FanoQueue *q;
+    ChainScratch *cs;
+    int idt;
+    unsigned periods, busy_periods, attempts, dropped;         // statistics of this lane
+    __device__ void period(bool active) {
+        periods++;
+        busy_periods += active ? 1u : 0u;
+    }
+    __device__ const unsigned char *next(unsigned &stop_after) {
+        stop_after = 0;
+        for (;;) {
+            const unsigned tail = *(volatile unsigned *)&q->tail;
+            unsigned h = *(volatile unsigned *)&q->head0;
+            if (h != tail) {                                   // attempt 0 of the next candidate nobody has started
+                if (atomicCAS(&q->head0, h, h + 1u) != h) continue;
+                FanoQueueEntry &x = q->ring[h & q->mask];
+                while (*(volatile unsigned *)&x.seq != h + 1u) __nanosleep(100);   // reserved, being written by a running kernel
+                __threadfence();
+                cs = *(ChainScratch *volatile *)&x.cs;
+                idt = 0;
+            } else {                                           // a jittered attempt of the oldest candidate that has any left
+                h = *(volatile unsigned *)&q->head1;
+                if (h == tail) return nullptr;
+                FanoQueueEntry &x = q->ring[h & q->mask];
+                if (*(volatile unsigned *)&x.seq != h + 1u) continue;       // not written yet, or the cursor has moved on
+                __threadfence();
+                ChainScratch *c = *(ChainScratch *volatile *)&x.cs;
+                __threadfence();
+                if (*(volatile unsigned *)&x.seq != h + 1u) continue;
+                const int na = *(volatile int *)&c->nattempts;
+                const int k = *(volatile int *)&c->next >= na ? na : atomicAdd(&c->next, 1);
+                if (k >= na) {                                 // nothing left to claim there: move the cursor on
+                    atomicCAS(&q->head1, h, h + 1u);
+                    continue;
+                }
+                cs = c;
+                idt = k;
+            }
+            if (cs->gate[idt] && *(volatile int *)&cs->best > idt) return cs->sym[idt];
+            cs->unfinished[idt] = 1;                           // never run: gated off, or a lower-numbered attempt has decoded
+            dropped++;
+            fano_settle(cs, 1);
+        }
+    }
+    __device__ bool abandon() const { return *(volatile int *)&cs->best < idt; }
+    __device__ void finish(const FanoResult &r) {
+        cs->ok[idt] = (r.rc == 0);
+        cs->unfinished[idt] = (r.rc == FANO_STOPPED);
+        cs->cycles[idt] = r.cycles;
+        for (int k = 0; k < 12; k++) cs->dec[idt][k] = r.data[k];
+        if (r.rc == FANO_STOPPED) dropped++;
+        else attempts++;
+        int count = 1;
+        if (r.rc == 0) {
+            atomicMin(&cs->best, idt);
+            // the attempts nobody has claimed yet all come after this one: the reference's loop never reaches them
+            const int na = cs->nattempts, k = atomicAdd(&cs->next, NJIT + 1);
+            for (int y = k; y < na; y++) cs->unfinished[y] = 1;
+            if (k < na) count += na - k;
+        }
+        fano_settle(cs, count);
+    }
+};
+
+// The pool: at most q->pool worker warps are alive at any time.  A warp that finds the pool complete leaves at once; a warp
+// whose lanes are all idle with the queue empty gives its place up FIRST and looks at the queue once more afterwards (a
+// producer may have added work, and the warps launched for that work may have found the pool complete and left), taking
+// the place back if there is something to do -- so work is never stranded, and nobody ever waits for work.
+__global__ void __launch_bounds__(32) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
-    const int e = (int)blockIdx.x * 32 + (int)threadIdx.x;
-    const bool mine = e < n;
-    const int cap = mine ? defer_list[e] : defer_list[0];
-    const Attempt &a = att0[cap];
-    const bool want = mine && a.gate && a.unfinished;         // (else the attempt already ran to its end in the round, or is gated off)
-    Job &job = jobs[cap];
-    FanoResult r;
-    fano_dense<false>(r, want, a.sym, &c_mettab[0][0], delta, maxcycles, 0, FirstHook{&job, &caps[cap], stats},
-                      FanoSmem::at(fano_smem, 512u));
-    if (!mine || (want && r.rc == 0)) return;                  // (a decode has been published by the hook)
-    if (want) job.cycles = r.cycles;                           // `cycles` keeps the last completed decoder call's count
-    if (quick) {                                               // wsprd.c:764-765: no jitter search, the candidate is done
-        atomicAdd(stats + 2, 1);
-        __threadfence();
-        *(volatile int *)&caps[cap].phase = PH_RESOLVE;
-    } else {
-        list2[atomicAdd(count2, 1)] = cap;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    smid &= 255u;
+    int mine = 0;
+    if (lane == 0) {
+        const int per_sm = *(volatile int *)&q->per_sm;
+        mine = per_sm <= 0 || atomicAdd(&q->sm_workers[smid], 1) < per_sm;     // (this SM has its share of workers: leave)
+        if (!mine) atomicSub(&q->sm_workers[smid], 1);
+        if (mine) {
+            mine = atomicAdd(&q->active, 1) < *(volatile int *)&q->pool;
+            if (!mine) {
+                atomicSub(&q->active, 1);
+                if (per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
+            }
+        }
+    }
+    mine = __shfl_sync(0xffffffffu, mine, 0);
+    if (!mine) return;
+    FanoQueueFeed feed{q, nullptr, 0, 0u, 0u, 0u, 0u};
+    while (mine) {
+        fano_run<false>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);
+        mine = 0;
+        if (lane == 0) {
+            atomicSub(&q->active, 1);
+            __threadfence();
+            const unsigned tail = *(volatile unsigned *)&q->tail;
+            if (*(volatile unsigned *)&q->head0 != tail || *(volatile unsigned *)&q->head1 != tail) {
+                mine = atomicAdd(&q->active, 1) < *(volatile int *)&q->pool;
+                if (!mine) atomicSub(&q->active, 1);
+            }
+        }
+        mine = __shfl_sync(0xffffffffu, mine, 0);
+    }
+    const unsigned busy = __reduce_add_sync(0xffffffffu, feed.busy_periods), att = __reduce_add_sync(0xffffffffu, feed.attempts),
+                   drop = __reduce_add_sync(0xffffffffu, feed.dropped);
+    if (lane == 0) {
+        if (*(volatile int *)&q->per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
+        atomicAdd(&q->st_warp_periods, (unsigned long long)feed.periods);
+        atomicAdd(&q->st_lane_periods, (unsigned long long)busy);
+        atomicAdd(&q->st_attempts, (unsigned long long)att);
+        atomicAdd(&q->st_dropped, (unsigned long long)drop);
+        atomicAdd(&q->st_warps, 1ull);
     }
 }
 
-void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *list2, int *count2, int *stats, const DecodeParams &p, cudaStream_t st) {
+void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
+                     ChainScratch *scratch, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p, cudaStream_t st) {
     if (n <= 0) return;
-    fano_attrs();
     const int nattempts = p.quickmode ? 1 : NJIT;
-    // WSPR_DEBUG_CHAIN_MAXCYCLES: experiment knob (wrong results!) to measure what the long Fano runs cost
-    static const unsigned dbg_maxcycles = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
-    // WSPR_CHAIN_PIECES: experiment knob (2 = two pieces per CTA); WSPR_CHAIN_STAGES=2: jitter-0 attempts first, 32 candidates
-    // per warp (k_chain_first), the 42 jittered attempts only for the candidates that fail it
-    static const int ppc = [] { const char *e = getenv("WSPR_CHAIN_PIECES"); int v = e ? atoi(e) : 1; return v >= 1 && v <= CHAIN_PIECES ? v : 1; }();
-    static const bool two_stage = [] { const char *e = getenv("WSPR_CHAIN_STAGES"); return e && e[0] == '2'; }();
-    const unsigned maxcycles = dbg_maxcycles ? dbg_maxcycles : p.maxcycles;
-    const int *count = nullptr;
-    if (two_stage) {
-        cudaMemsetAsync(count2, 0, sizeof(int), st);
-        k_chain_first<<<(n + 31) / 32, 32, FANO_WARP_SMEM_BYTES, st>>>(jobs, caps, att0, defer_list, n, p.delta, maxcycles, p.quickmode,
-                                                                      list2, count2, stats);
-        LAUNCHED();
-        if (p.quickmode) return;
-        defer_list = list2;                                    // stage 2: the candidates whose jitter-0 attempt failed
-        count = count2;
-    }
-    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, defer_list, count, two_stage ? 1 : 0, scratch, p.np, p.stride,
-                                                      p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
+    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, caps, defer_list, scratch, stats, host_done, nattempts, p.np,
+                                                      p.stride, p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
     LAUNCHED();
-    const int nctas = n + (nattempts > 32 ? (n + 1) / 2 : 0);
-    static const bool pipe = [] { const char *e = getenv("WSPR_FANO_PIPE"); return e && e[0] == '1'; }();
-    if (pipe)
-        k_chain_fano<true><<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
-            jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
-    else
-        k_chain_fano<false><<<(nctas + ppc - 1) / ppc, 32 * ppc, (size_t)ppc * FANO_WARP_SMEM_BYTES, st>>>(
-            jobs, caps, defer_list, scratch, n, nctas, count, nattempts, p.delta, maxcycles, stats);
+    k_fano_enqueue<<<1, 256, 0, st>>>(queue, scratch, defer_list, n);
     LAUNCHED();
 }
 
+int fano_warp_smem_bytes() { return FANO_WARP_SMEM_BYTES; }
+void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st) {
+    if (nwarps <= 0) return;
+    k_fano_workers<<<nwarps, 32, FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta, p.maxcycles);
+    LAUNCHED();
+}
+
+// the Fano kernel on caller-supplied soft symbols (wspr_fano_batch): solo & 1: one attempt per warp (latency of a lone
+// attempt), solo & 4: the decode instantiation instead of the exact one
 __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restrict__ symbols, int n, int delta,
                                                   unsigned maxcycles, unsigned stop_after, int solo, int *__restrict__ rc,
                                                   unsigned *__restrict__ metric, unsigned *__restrict__ cycles,
                                                   unsigned *__restrict__ maxnp, unsigned char *__restrict__ data,
-                                                  unsigned long long *__restrict__ clocks, unsigned char *__restrict__ gmem) {
+                                                  unsigned long long *__restrict__ clocks) {
     extern __shared__ __align__(16) unsigned char fano_smem[];
-    const bool fast = (solo & 4) != 0, pipe = (solo & 8) != 0;
-    solo &= 3;
+    const bool fast = (solo & 4) != 0;
+    solo &= 1;
     const int i = solo ? (int)blockIdx.x : (int)(blockIdx.x * 32 + threadIdx.x);
     const bool want = i < n && (!solo || threadIdx.x == 0);
-    FanoResult r;
     const long long t0 = clock64();
-    const unsigned char *sym = symbols + (size_t)(want ? i : 0) * NSYM;
-    if (gmem)
-        fano_dense<true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                         FanoGmem{gmem + (size_t)blockIdx.x * FANO_WARP_SMEM_BYTES, 512u});
-    else if (fast && pipe)
-        fano_dense<false, true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                                FanoSmem::at(fano_smem, 512u));
-    else if (pipe)
-        fano_dense<true, true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                               FanoSmem::at(fano_smem, 512u));
-    else if (fast)                                             // the instantiation the decode kernels use
-        fano_dense<false>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                          FanoSmem::at(fano_smem, 512u));
-    else
-        fano_dense<true>(r, want, sym, &c_mettab[0][0], delta, maxcycles, stop_after, FanoNoStop(),
-                         FanoSmem::at(fano_smem, 512u));
+    FanoOneShot feed{want ? symbols + (size_t)i * NSYM : nullptr, stop_after, {}};
+    if (fast) fano_run<false>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);   // what the decode kernels run
+    else fano_run<true>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);
     if (!want) return;
+    const FanoResult &r = feed.res;
     if (clocks) clocks[i] = (unsigned long long)(clock64() - t0);
     rc[i] = r.rc;
     metric[i] = r.metric;
@@ -1258,15 +1267,13 @@ __global__ void __launch_bounds__(32) k_fano_test(const unsigned char *__restric
     maxnp[i] = r.maxnp;
     for (int k = 0; k < 12; k++) data[(size_t)i * 12 + k] = r.data[k];
 }
-size_t fano_warp_scratch_bytes() { return FANO_WARP_SMEM_BYTES; }
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
-                      unsigned char *gmem, cudaStream_t st) {
+                      cudaStream_t st) {
     if (n <= 0) return;
-    fano_attrs();
     const int blocks = (solo & 1) ? n : (n + 31) / 32;
-    k_fano_test<<<blocks, 32, gmem ? 0 : FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 13, rc, metric,
-                                                                   cycles, maxnp, data, clocks, gmem);
+    k_fano_test<<<blocks, 32, FANO_WARP_SMEM_BYTES, st>>>(symbols, n, delta, maxcycles, stop_after, solo & 5, rc, metric, cycles,
+                                                         maxnp, data, clocks);
     LAUNCHED();
 }
 
@@ -1608,51 +1615,10 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
     LAUNCHED();
 }
 
-// Opt in to > 48 KB of dynamic shared memory, and ask for the LARGEST shared-memory carve-out for every kernel that shares
-// an SM with the long Fano runs.  An SM cannot change its L1/shared split while a CTA is resident: with the driver's
-// per-kernel default a one-warp Fano CTA (84 KB) pins its SM at the smallest split that holds it for the 100+ ms it runs,
-// and the bulk kernels (K4: 2 x 47 KB) then cannot be placed on that SM at all -- measured with tools/exp_interference.py:
-// one such CTA per SM serialises the whole decode behind it.  With one common split nothing ever has to wait for an SM to
-// drain.  (WSPR_CARVEOUT=default restores the driver's choice, for A/B measurements.)
-static void fano_attrs() {
-    static std::atomic<bool> done{false};
-    if (done.load()) return;
-    cudaFuncSetAttribute(k_fano_round, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_fano_test, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_first, cudaFuncAttributeMaxDynamicSharedMemorySize, FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chain_fano<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_PIECES * FANO_WARP_SMEM_BYTES);
+// Opt in to > 48 KB of dynamic shared memory (k_sync_freqs_shared).  Function attributes belong to the device that is
+// current, so this runs once per device (wspr_decode.cu calls it when it sets a device up).
+void init_kernel_attributes() {
     cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
-    // WSPR_CARVEOUT = default | chain | max | <percent> : which kernels ask for which shared-memory carve-out (experiment knob)
-    const char *e = getenv("WSPR_CARVEOUT");
-    const char mode = e ? e[0] : 'd';
-    int mx = cudaSharedmemCarveoutMaxShared;
-    const bool numeric = mode >= '0' && mode <= '9';
-    if (numeric) mx = atoi(e);
-    if (mode == 'c' || mode == 'm' || numeric) {
-        cudaFuncSetAttribute(k_fano_round, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_fano_test, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_chain_fano<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_chain_fano<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    }
-    if (mode == 'm' || numeric) {
-        cudaFuncSetAttribute(k_jitter_soft, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_spectrogram, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_coarse, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sync_lags, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_pick_lag, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_pick_freq, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sync_freqs, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sub_phase, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sub_ref, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_sub_lpf<WSPR_LPF_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_plan, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_collect, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    }
-    done.store(true);
 }
-void init_kernel_attributes() { fano_attrs(); }
 
 }  // namespace wspr

@@ -57,14 +57,16 @@ struct DecodeParams {
     const char *preload;    // device [32768][13]: callsign hash table loaded from hashtable.txt (options.usehashtable), or null
 };
 // wsprd.c:524-531
-__host__ __device__ inline int pass_maxdrift(int ipass) { return ipass == 2 ? 0 : 4; }
-__host__ __device__ inline float pass_minsync2(int ipass) { return ipass == 2 ? 0.10f : 0.12f; }
+// (only passes 0/1 and 2 assign them, so later passes keep the values of pass 2)
+__host__ __device__ inline int pass_maxdrift(int ipass) { return ipass >= 2 ? 0 : 4; }
+__host__ __device__ inline float pass_minsync2(int ipass) { return ipass >= 2 ? 0.10f : 0.12f; }
 
 // Scheduling.  The reference walks the candidates of one capture strictly in order (a decode is subtracted from the
 // samples before the next candidate is looked at), but captures are independent.  Every capture therefore runs its
 // own little state machine and a *round* advances every capture that is ready by one candidate; a capture whose
 // Fano attempt needs more than fano_budget cycles (or that must go through the 42-attempt jitter search) is parked
-// (PH_WAIT) while a side stream finishes it, and rejoins a later round (PH_RESOLVE) -- it never holds the others up.
+// (PH_WAIT) while the pool of Fano worker warps finishes it, and rejoins a later round (PH_RESOLVE) -- it never holds the
+// others up.
 enum Phase { PH_SETUP = 0, PH_READY = 1, PH_WAIT = 2, PH_RESOLVE = 3, PH_DONE = 4 };
 
 // the candidate a capture is currently working on (at most one per capture; indexed by capture)
@@ -115,14 +117,46 @@ struct CapState {
     unsigned char chan[NSYM + 2];
 };
 
-// soft symbols and gates of the 43 attempts of one parked candidate (attempt 0 = jitter 0)
+// soft symbols, gates and results of the 43 attempts of a capture's parked candidate (attempt 0 = jitter 0); one record per
+// capture (a capture has at most one candidate parked at a time), filled by k_jitter_soft, worked off by the Fano workers.
+// The records live in memory owned by the per-device Fano service and are never freed while the process runs: a worker may
+// still look at a record (and find nothing left to claim in it) after its candidate has been settled.
 struct ChainScratch {
     int best;           // lowest attempt number that has decoded so far
-    int done;           // CTAs of the candidate that have finished
+    int done;           // attempts accounted for (decoded, timed out, abandoned or skipped)
+    int next;           // next jittered attempt to hand out (>= nattempts: nothing left to claim)
+    int nattempts;      // 43, or 1 in quick mode
+    Job *job;           // where the lane that accounts for the last attempt leaves the outcome ...
+    int *phase;         // ... before it hands the capture back to the rounds (CapState::phase = PH_RESOLVE)
+    int *stats;         // [0] settled by the full-budget jitter-0 run, [1] by a jittered attempt, [2] never decoded
+    int *host_done;     // mapped host counter of the context: captures handed back so far
     int gate[NJIT], ok[NJIT], unfinished[NJIT];
     unsigned cycles[NJIT];
     unsigned char dec[NJIT][12];
     unsigned char sym[NJIT][NSYM + 2];
+};
+
+// Device-wide queue of parked candidates (one per GPU, shared by every context of the process).  Producers reserve slots
+// with one atomicAdd on `tail` and stamp each entry with its sequence number once it is written.  Two cursors walk the
+// same ring: head0 hands out attempt 0 of each candidate (one pop per candidate), head1 points at the oldest candidate
+// that may still have jittered attempts to claim (ChainScratch::next) and moves on when there are none.  Attempt 0 of
+// every queued candidate is handed out before any jittered attempt.  `active`/`pool`: worker warps alive / allowed.
+struct FanoQueueEntry {
+    ChainScratch *cs;
+    unsigned seq;       // slot index + 1 once the entry is valid
+    unsigned pad;
+};
+struct FanoQueue {
+    unsigned head0, head1, tail;
+    int active, pool;
+    unsigned mask;      // capacity - 1 (power of two)
+    int overflow;       // a producer found the ring full (the decode reports an error)
+    int per_sm;         // worker warps allowed on one SM (0: no limit)
+    FanoQueueEntry *ring;
+    // statistics (wspr_fano_stats): housekeeping periods (256 loop trips) worker warps were alive for / their lanes had an
+    // attempt in, attempts decoded to the end, attempts skipped or abandoned, worker warps started
+    unsigned long long st_warp_periods, st_lane_periods, st_attempts, st_dropped, st_warps;
+    int sm_workers[256];
 };
 
 struct Counters {
@@ -157,11 +191,15 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
 // jitter-0 Fano attempts of the round (budgeted) and their triage into the resolve list / the deferred list
 void launch_fano_round(Attempt *att0, const int *job_list, int njobs, const DecodeParams &p, cudaStream_t st);
 void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *job_list, int njobs, int *res_list,
-                    int *defer_list, int *defer_count, Counters *cnt, const DecodeParams &p, cudaStream_t st);
-// side-stream completion of deferred candidates: full-budget jitter-0 Fano, then the jitter search (wsprd.c:741-766)
-// list2 / count2: device list (n entries) and counter for the candidates that go on to the jitter search
-void launch_deferred(const float *I, const float *Q, Job *jobs, Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *list2, int *count2, int *stats, const DecodeParams &p, cudaStream_t st);
+                    int *defer_list, Counters *cnt, const DecodeParams &p, cudaStream_t st);
+// parked candidates (wsprd.c:741-766): soft symbols of the jittered attempts into scratch[capture], then all attempts of the
+// n candidates into the device queue; launch_fano_workers starts up to `nwarps` worker warps on `st` (they leave at once
+// when the pool is already complete, and when the queue runs dry)
+void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
+                     ChainScratch *scratch, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p, cudaStream_t st);
+void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st);
+void init_kernel_attributes();               // per device: opt-in to > 48 KB of dynamic shared memory
+int fano_warp_smem_bytes();                  // shared memory one worker warp holds
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
                     const DecodeParams &p, cudaStream_t st);
 void launch_subtract(float *I, float *Q, const CapState *caps, const int *sub_list, int nsub_max, const Counters *cnt,
@@ -175,8 +213,7 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
 
 void launch_fano_test(const unsigned char *symbols, int n, int delta, unsigned maxcycles, unsigned stop_after, int solo, int *rc,
                       unsigned *metric, unsigned *cycles, unsigned *maxnp, unsigned char *data, unsigned long long *clocks,
-                      unsigned char *gmem, cudaStream_t st);
-size_t fano_warp_scratch_bytes();
+                      cudaStream_t st);
 
 // front end (rtlsdr_wsprd.c:126-244)
 void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t stream_stride_bytes, uint4 *moments, float *I,

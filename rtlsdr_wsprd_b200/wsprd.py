@@ -115,6 +115,8 @@ def library():
     lib.wspr_kernel_launches.restype = C.c_ulonglong
     lib.wspr_ctx_spectrogram.argtypes = [vp, vp]
     lib.wspr_ctx_candidates.argtypes = [vp, C.c_int, vp, vp, vp]
+    if hasattr(lib, "wspr_fano_stats"):
+        lib.wspr_fano_stats.argtypes = [C.c_int, vp, C.c_int]
     lib.wspr_fano_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.wspr_decimate_batch.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_int, C.c_int]
     lib.wspr_decimate_device.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int]
@@ -354,6 +356,15 @@ def fano_batch(symbols, delta=60, maxcycles=10000, stop_after=0, solo=False):
                                      out["maxnp"].ctypes.data, out["data"].ctypes.data, out["clocks"].ctypes.data),
            "wspr_fano_batch")
     return out
+
+
+def fano_pool_stats(device=-1, reset=False):
+    """Counters of the device's pool of Fano worker warps (wspr_fano_stats): dict with pool, fano_sms, lane utilisation..."""
+    out = (C.c_ulonglong * 8)()
+    _check(library().wspr_fano_stats(int(device), out, int(bool(reset))), "wspr_fano_stats")
+    v = [int(x) for x in out]
+    return {"pool_warps": v[0], "fano_sms": v[1], "warp_periods": v[2], "lane_utilisation": round(v[3] / (32.0 * v[2]), 4) if v[2] else None,
+            "attempts_run": v[4], "attempts_dropped": v[5], "worker_warps_started": v[6]}
 
 
 def decimate_batch(raw, n_iq=None, max_out=NSAMP, device=-1):

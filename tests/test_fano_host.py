@@ -1,8 +1,8 @@
 """The device Fano loop (rtlsdr_wsprd_b200/csrc/wspr_fano.cuh) compiled for the HOST (tools/fano_host_check.cpp: same
 template source, one lane, scratch in ordinary memory) against fano() of the oracle on random soft-symbol vectors from
-clean to hopeless, time-outs included.  Covers the logic of all four instantiations -- exact / decode (time-out test every
-256 trips, maxnp not tracked) x plain / pipelined (records fetched a trip ahead) -- without a GPU; the GPU suite repeats the
-comparison for the instantiations the library runs."""
+clean to hopeless, time-outs included.  Covers the logic of both instantiations -- exact / decode (time-out test every
+256 trips, maxnp not tracked) -- and the re-arming of a lane (several attempts back to back through one lane, which is what
+the queue-fed worker warps do) without a GPU; the GPU suite repeats the comparison for the kernels the library runs."""
 import ctypes as C
 import os
 import subprocess
@@ -25,8 +25,8 @@ def host_fano(tmp_path_factory):
     except FileNotFoundError:
         pytest.skip("g++ not available")
     lib = C.CDLL(out)
-    lib.fano_host.argtypes = [C.c_int, UP, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint),
-                              C.POINTER(C.c_uint), UP]
+    lib.fano_host.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -56,12 +56,20 @@ def oracle_fano(v, maxcycles, delta=60):
     return rc, met.value, cyc.value, mx.value, bytes(data)[:10]
 
 
+def run_host_many(lib, variant, vecs, maxcycles, delta=60, stop_after=0):
+    """All vectors through ONE lane back to back (the lane re-arms between attempts)."""
+    n = len(vecs)
+    sym = np.ascontiguousarray(np.stack(vecs), dtype=np.uint8)
+    rc, met, cyc, mx = np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    data = np.zeros((n, 12), np.uint8)
+    ret = lib.fano_host(variant, sym.ctypes.data, n, delta, maxcycles, stop_after, rc.ctypes.data, met.ctypes.data,
+                        cyc.ctypes.data, mx.ctypes.data, data.ctypes.data)
+    assert ret == 0, ret
+    return [(int(rc[i]), int(met[i]), int(cyc[i]), int(mx[i]), bytes(data[i])[:10]) for i in range(n)]
+
+
 def run_host(lib, variant, v, maxcycles, delta=60, stop_after=0):
-    met, cyc, mx = C.c_uint(), C.c_uint(), C.c_uint()
-    data = (C.c_ubyte * 12)()
-    s = v.copy()
-    rc = lib.fano_host(variant, s.ctypes.data_as(UP), delta, maxcycles, stop_after, C.byref(met), C.byref(cyc), C.byref(mx), data)
-    return rc, met.value, cyc.value, mx.value, bytes(data)[:10]
+    return run_host_many(lib, variant, [v], maxcycles, delta, stop_after)[0]
 
 
 @pytest.mark.parametrize("maxcycles,count", [(300, 160), (10000, 16)])
@@ -69,16 +77,15 @@ def test_host_build_of_device_fano_matches_oracle(host_fano, maxcycles, count):
     vecs = vectors(count, 42 + maxcycles)
     want = [oracle_fano(v, maxcycles) for v in vecs]
     assert any(x[0] == 0 for x in want) and any(x[0] != 0 for x in want)
-    for variant in (0, 2):                       # exact instantiations: every field as fano.c produces it
-        for v, x in zip(vecs, want):
-            got = run_host(host_fano, variant, v, maxcycles)
-            assert got[:4] == x[:4], (variant, got, x)
+    for many in (False, True):                   # one attempt per call / all attempts through one re-arming lane
+        run = (lambda var: run_host_many(host_fano, var, vecs, maxcycles)) if many else \
+              (lambda var: [run_host(host_fano, var, v, maxcycles) for v in vecs])
+        for got, x in zip(run(0), want):         # exact instantiation: every field as fano.c produces it
+            assert got[:4] == x[:4], (many, got, x)
             if x[0] == 0:
                 assert got[4] == x[4]
-    for variant in (1, 3):                       # decode instantiations: rc, cycles; metric and bytes when decoded
-        for v, x in zip(vecs, want):
-            got = run_host(host_fano, variant, v, maxcycles)
-            assert (got[0], got[2]) == (x[0], x[2]), (variant, got, x)
+        for got, x in zip(run(1), want):         # decode instantiation: rc, cycles; metric and bytes when decoded
+            assert (got[0], got[2]) == (x[0], x[2]), (many, got, x)
             if x[0] == 0:
                 assert got[1] == x[1] and got[4] == x[4]
 
@@ -88,13 +95,10 @@ def test_host_build_small_delta_and_budget(host_fano):
     vecs = vectors(48, 7)
     for v in vecs:
         x = oracle_fano(v, 200, delta=7)
-        for variant in (0, 2):
-            assert run_host(host_fano, variant, v, 200, delta=7)[:4] == x[:4]
-    for v in vecs:
-        full = run_host(host_fano, 1, v, 10000)
-        for variant in (1, 3):
-            got = run_host(host_fano, variant, v, 10000, stop_after=2048)
-            if got[0] == 2:
-                assert full[2] > 2048
-            else:
-                assert (got[0], got[2], got[4]) == (full[0], full[2], full[4])
+        assert run_host(host_fano, 0, v, 200, delta=7)[:4] == x[:4]
+    fulls = run_host_many(host_fano, 1, vecs, 10000)
+    for got, full in zip(run_host_many(host_fano, 1, vecs, 10000, stop_after=2048), fulls):
+        if got[0] == 2:
+            assert full[2] > 2048
+        else:
+            assert (got[0], got[2], got[4]) == (full[0], full[2], full[4])
