@@ -337,6 +337,7 @@ def run_captures(args):
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = w.kernel_launches()
+    w.fano_pool_stats(local, reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()                                   # device idle here (barrier above): default-stream events bracket all streams
@@ -344,6 +345,7 @@ def run_captures(args):
     torch.cuda.synchronize()
     ev1.record()
     barrier()
+    pool_stats = w.fano_pool_stats(local)
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
     launches = w.kernel_launches() - launches0
@@ -433,7 +435,7 @@ def run_captures(args):
                 "run": {"l2": "inputs (%.2f GB/step/GPU) larger than L2" % (2 * total * NSAMP * 4 / 1e9),
                         "parallelism": "independent per-GPU batches, no collective on the data path",
                         "batches_in_flight": args.depth, "captures_per_call": ncap, "calls_per_step": nbatch,
-                        "fano_pool": os.environ.get("WSPR_FANO_POOL", "default"), "fano_sms": os.environ.get("WSPR_FANO_SMS", "default")},
+                        "fano_pool": pool_stats},
                 "e2e": {"value": round(total_caps / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": 2 * total * NSAMP * 4,
                         "d2h_bytes_per_step": total * (w.MAX_UNIQUES * 80 + 4)},
                 "gpu_launches": int(launches), "spots_per_step": nspots, "wall_ms_per_step": round(wall_ms / args.steps, 3),

@@ -21,6 +21,7 @@ extern "C" {
 #define WSPR_OK 0
 #define WSPR_ERR_CUDA (-2)
 #define WSPR_ERR_ARG (-3)
+#define WSPR_ERR_LIMIT (-4) /* an internal capacity was exceeded (results would differ from the reference's): nothing is returned */
 #define WSPR_MAX_UNIQUES 100 /* MAX_UNIQUES, wsprd/wsprd.h:41 */
 #define WSPR_CAPTURE_SAMPLES 45000
 
@@ -65,6 +66,8 @@ int wspr_decode(float *idat, float *qdat, int samples, struct decoder_options op
 void sync_and_demodulate(float *id, float *qd, long np, unsigned char *symbols, float *freq, int ifmin, int ifmax,
                          float fstep, int *shift, int lagmin, int lagmax, int lagstep, float *drift, int symfac,
                          float *sync, int mode);
+/* wsprd/wsprd.h:92-98 (exported by the reference, never called by it) */
+void subtract_signal(float *id, float *qd, long np, float f0, int shift, float drift, const unsigned char *channel_symbols);
 /* wsprd/wsprd.h:99-105 */
 void subtract_signal2(float *id, float *qd, long np, float f0, int shift, float drift,
                       const unsigned char *channel_symbols);

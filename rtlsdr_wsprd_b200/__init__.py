@@ -7,10 +7,10 @@ every compute call raises ``WsprCudaError`` when the library or a CUDA device is
 """
 from .wsprd import (DecoderOptions, DecoderResults, RESULT_DTYPE, CAND_DTYPE, MAX_UNIQUES, NSAMP, WsprCudaError,
                     default_options, library, library_path, wspr_decode, decode_batch, BatchDecoder, PipelinedDecoder, decimate_batch,
-                    decimate_device, FrontEnd, fano_batch, fano_pool_stats, spot_line, print_spots_lines, wsprnet_urls, read_iq_file, read_c2_file, write_iq_file, normalise_half,
+                    decimate_device, FrontEnd, fano_batch, fano_pool_stats, spot_line, print_spots_lines, wsprnet_urls, read_iq_file, read_c2_file, write_iq_file, write_c2_file, load_capture_files, normalise_half,
                     kernel_launches, build_library)
 
 __all__ = ["DecoderOptions", "DecoderResults", "RESULT_DTYPE", "CAND_DTYPE", "MAX_UNIQUES", "NSAMP", "WsprCudaError",
            "default_options", "library", "library_path", "wspr_decode", "decode_batch", "BatchDecoder", "PipelinedDecoder",
-           "decimate_batch", "decimate_device", "FrontEnd", "fano_batch", "fano_pool_stats", "spot_line", "print_spots_lines", "wsprnet_urls", "read_iq_file", "read_c2_file", "write_iq_file",
+           "decimate_batch", "decimate_device", "FrontEnd", "fano_batch", "fano_pool_stats", "spot_line", "print_spots_lines", "wsprnet_urls", "read_iq_file", "read_c2_file", "write_iq_file", "write_c2_file", "load_capture_files",
            "normalise_half", "kernel_launches", "build_library"]

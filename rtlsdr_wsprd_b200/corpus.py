@@ -140,3 +140,91 @@ def make_raw_stream(config_id, index, n_iq, f0=50.0, snr=-10.0, symbols=None, si
         out[2 * lo:2 * hi:2] = v[0]
         out[2 * lo + 1:2 * hi:2] = v[1]
     return out
+
+
+# ---- BASELINE config 4 at full size: raw streams synthesised from a counter-based INTEGER generator -------------------
+# 256 streams x 288e6 IQ pairs are 147 GB: they are generated on the device, and the parity streams are regenerated on the
+# host.  Every step below is 64-bit integer arithmetic with wrap-around, written against an array module `xp` (numpy or
+# torch), so that both produce the same bytes: noise = sum of four hash bytes per component (Irwin-Hall, sigma = 20.06 LSB),
+# signal = a 32-bit phase accumulator through a 1024-entry cosine table in Q14.
+RAW_FS = 2400000.0
+RAW_SYMBOL = 256 * 6400                              # raw samples per WSPR symbol (375 sps x 6400)
+_M64 = (1 << 64) - 1
+
+
+def _s64(v):
+    """python int -> the signed 64-bit value with the same bit pattern"""
+    v &= _M64
+    return v - (1 << 64) if v >> 63 else v
+
+
+def raw_stream_plan(index, symbols_fn, snr=-10.0, sigma_lsb=20.06):
+    """One signal per stream: tone at -600000 + f0 Hz so that the fs/4 mixer lands it at f0."""
+    rng = rng_for(4 + 1000, index)
+    call, grid = STATIONS[int(rng.integers(len(STATIONS)))]
+    pwr = POWERS[int(rng.integers(len(POWERS)))]
+    msg = "%s %s %d" % (call, grid, pwr)
+    f0, dt0 = float(rng.uniform(-100, 100)), float(rng.uniform(-0.5, 0.5))
+    sym = np.asarray(symbols_fn(msg), dtype=np.int64)
+    amp = float(np.sqrt(10.0 ** (snr / 10.0) * 2.0 * sigma_lsb * sigma_lsb * 2500.0 / RAW_FS))
+    inc4 = [int(round((-600000.0 + f0 + (s - 1.5) * DF) / RAW_FS * 2.0 ** 32)) & 0xffffffff for s in range(4)]
+    inc = [inc4[int(s)] for s in sym]
+    base, acc = [], 0
+    for k in range(NSYM):                            # phase at the first sample of symbol k
+        base.append(acc)
+        acc = (acc + inc[k] * RAW_SYMBOL) & 0xffffffff
+    return dict(index=index, message=msg, f0=f0, dt0=dt0, snr=snr, start=int(np.floor((2.0 + dt0) * RAW_FS)),
+                amp_q14=int(round(amp * 16384.0)), inc=inc, base=base, key=_s64(0x9E3779B97F4A7C15 * (index + 1)))
+
+
+_COS_Q14 = np.round(np.cos(2.0 * np.pi * np.arange(1024) / 1024.0) * 16384.0).astype(np.int64)
+
+
+def synth_raw_stream(xp, plan, n_iq, out=None, device=None, block=1 << 23):
+    """uint8[2 * n_iq] interleaved (I, Q) of plan's stream.  xp = numpy (host) or torch (out: a uint8 device tensor view)."""
+    is_np = xp is np
+    if is_np:
+        res = np.empty(2 * n_iq, np.uint8) if out is None else out
+        mk = lambda a: np.asarray(a, dtype=np.int64)
+        arange = lambda lo, hi: np.arange(lo, hi, dtype=np.int64)
+        clamp = lambda a, lo, hi: np.clip(a, lo, hi)
+        old = np.seterr(over="ignore")
+    else:
+        res = out
+        mk = lambda a: xp.as_tensor(np.asarray(a, dtype=np.int64), device=device)
+        arange = lambda lo, hi: xp.arange(lo, hi, dtype=xp.int64, device=device)
+        clamp = lambda a, lo, hi: xp.clamp(a, lo, hi)
+    inc_t, base_t, cos_t = mk(plan["inc"] + [0]), mk(plan["base"] + [0]), mk(_COS_Q14)
+    c1, c2 = _s64(0xBF58476D1CE4E5B9), _s64(0x94D049BB133111EB)
+
+    def lsr(x, s):                                   # logical shift right of a signed 64-bit array
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    for lo in range(0, n_iq, block):
+        hi = min(lo + block, n_iq)
+        n = arange(lo, hi)
+        x = n + plan["key"]                          # splitmix64 finaliser of (sample index + stream key)
+        x = (x ^ lsr(x, 30)) * c1
+        x = (x ^ lsr(x, 27)) * c2
+        x = x ^ lsr(x, 31)
+        ni = ((x & 255) + ((x >> 8) & 255) + ((x >> 16) & 255) + ((x >> 24) & 255) - 510) * 139
+        nq = (((x >> 32) & 255) + ((x >> 40) & 255) + ((x >> 48) & 255) + (lsr(x, 56) & 255) - 510) * 139
+        rel = n - plan["start"]
+        k = rel // RAW_SYMBOL if is_np else xp.div(rel, RAW_SYMBOL, rounding_mode="floor")
+        on = (k >= 0) & (k < NSYM)
+        kc = clamp(k, 0, NSYM - 1)
+        ph = (base_t[kc] + inc_t[kc] * (rel - kc * RAW_SYMBOL)) & 0xffffffff
+        amp = on * plan["amp_q14"] if is_np else on.to(xp.int64) * plan["amp_q14"]
+        si = (amp * cos_t[(ph >> 22) & 1023]) >> 18
+        sq = (amp * cos_t[((ph >> 22) + 768) & 1023]) >> 18         # sin = cos(phase - 90 deg)
+        vi = clamp((130560 + 512 + ni + si) >> 10, 0, 255)
+        vq = clamp((130560 + 512 + nq + sq) >> 10, 0, 255)
+        if is_np:
+            res[2 * lo:2 * hi:2] = vi.astype(np.uint8)
+            res[2 * lo + 1:2 * hi:2] = vq.astype(np.uint8)
+        else:
+            res[2 * lo:2 * hi:2] = vi.to(xp.uint8)
+            res[2 * lo + 1:2 * hi:2] = vq.to(xp.uint8)
+    if is_np:
+        np.seterr(**old)
+    return res

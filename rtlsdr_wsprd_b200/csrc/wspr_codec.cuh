@@ -355,6 +355,7 @@ struct ListHashStore {
     int *count;
     int cap;
     const char *preload;           // [32768][13] calls read from hashtable.txt (reference -H, wsprd.c:481-494), or null
+    int *overflow;                 // set when an entry had to be dropped because the list is full (the decode reports it)
     WHD const char *get(int h) const {
         for (int i = *count - 1; i >= 0; i--)
             if (e[i].h == h) return e[i].call;
@@ -363,7 +364,10 @@ struct ListHashStore {
     WHD HashEntry *slot(int h) {
         for (int i = 0; i < *count; i++)
             if (e[i].h == h) return &e[i];
-        if (*count >= cap) return nullptr;
+        if (*count >= cap) {
+            if (overflow) *overflow = 1;
+            return nullptr;
+        }
         HashEntry *n = &e[(*count)++];
         n->h = h;
         n->call[0] = 0;

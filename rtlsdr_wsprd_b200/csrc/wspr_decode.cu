@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <sched.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/file.h>
 #include <string.h>
 #include <time.h>
 
@@ -456,7 +458,28 @@ static int wait_parked(wspr_ctx *c, int seen, int want) {
 }
 
 // ---- options.usehashtable (reference -H): hashtable.txt in the CWD, wsprd.c:481-494 and :842-852 ----
+// Several contexts (host threads) and several ranks may decode with -H in the same CWD: the file is read when a decode
+// starts and rewritten when it ends, each under a process mutex plus an advisory lock on hashtable.txt.lock, and the rewrite
+// goes through a temporary file and rename() so that a reader never sees a half-written table.  Between its read and its
+// write-back a decode does not hold the lock; the write-back therefore re-reads the file and merges this decode's
+// additions into it, so entries other decodes added in the meantime are kept.
 constexpr int HT_SIZE = 32768;                                // HASHTAB_SIZE, wsprd/wsprd.h
+static std::mutex g_ht_mu;
+struct HtFileLock {
+    int fd;
+    HtFileLock() {
+        g_ht_mu.lock();
+        fd = open("hashtable.txt.lock", O_CREAT | O_RDWR, 0644);
+        if (fd >= 0) flock(fd, LOCK_EX);
+    }
+    ~HtFileLock() {
+        if (fd >= 0) {
+            flock(fd, LOCK_UN);
+            close(fd);
+        }
+        g_ht_mu.unlock();
+    }
+};
 struct HostHashTables {
     std::vector<char> calls, locs;                            // [32768][13], [32768][5]
     HostHashTables() : calls((size_t)HT_SIZE * CALL_LEN, 0), locs((size_t)HT_SIZE * LOC_LEN, 0) {}
@@ -477,12 +500,15 @@ static void hashtable_read(HostHashTables &t) {
     fclose(f);
 }
 static void hashtable_write(const HostHashTables &t) {
-    FILE *f = fopen("hashtable.txt", "w");
+    char tmp[64];
+    snprintf(tmp, sizeof tmp, "hashtable.txt.%ld.tmp", (long)getpid());
+    FILE *f = fopen(tmp, "w");
     if (!f) return;
     for (int i = 0; i < HT_SIZE; i++)
         if (t.calls[(size_t)i * CALL_LEN] != 0)
             fprintf(f, "%5d %s %s\n", i, t.calls.data() + (size_t)i * CALL_LEN, t.locs.data() + (size_t)i * LOC_LEN);
     fclose(f);
+    rename(tmp, "hashtable.txt");
 }
 // entries the captures added during the decode, merged in capture order (one capture = the reference's semantics; with
 // several captures in a batch every capture saw the table as it was on entry, and later captures win on write-back)
@@ -490,6 +516,8 @@ static int hashtable_merge(wspr_ctx *c, HostHashTables &t) {
     std::vector<CapState> caps(c->ncap);
     CK(cudaMemcpyAsync(caps.data(), c->caps, (size_t)c->ncap * sizeof(CapState), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    HtFileLock lock;
+    hashtable_read(t);                                        // (what other decodes wrote since this one started)
     for (const CapState &cs : caps)
         for (int i = 0; i < cs.nhash && i < HASH_CAP; i++) {
             const HashEntry &e = cs.hash[i];
@@ -497,6 +525,7 @@ static int hashtable_merge(wspr_ctx *c, HostHashTables &t) {
             snprintf(t.calls.data() + (size_t)e.h * CALL_LEN, CALL_LEN, "%s", e.call);
             if (e.loc[0]) snprintf(t.locs.data() + (size_t)e.h * LOC_LEN, LOC_LEN, "%s", e.loc);
         }
+    hashtable_write(t);
     return WSPR_OK;
 }
 
@@ -508,7 +537,10 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     HostHashTables *ht = nullptr;
     if (o.usehashtable && ncap > 0) {
         ht = new HostHashTables();
-        hashtable_read(*ht);
+        {
+            HtFileLock lock;
+            hashtable_read(*ht);
+        }
         cudaError_t e = c->preload ? cudaSuccess : cudaMalloc((void **)&c->preload, ht->calls.size());
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->preload, ht->calls.data(), ht->calls.size(), cudaMemcpyHostToDevice, c->st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
@@ -581,7 +613,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             nres_max = c->h_cnt->nres;
             if (ndefer > 0) {                                 // finish them off the critical path
                 c->deferred += ndefer;
-                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer, c->scratch, c->stats, c->h_done,
+                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer, c->scratch, c->tabs, c->stats, c->h_done,
                                 c->svc->queue, p, c->st);
                 CK(cudaEventRecord(c->ev_fano, c->st));
                 cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];
@@ -596,7 +628,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             launch_subtract(c->I, c->Q, c->caps, c->sub_list, nres_max, c->cnt, c->phi0, c->ref, c->cprod, p, c->st);
         CK(cudaGetLastError());
     }
-    launch_finish(c->caps, c->spots, c->nres, ncap, c->st);
+    launch_finish(c->caps, c->spots, c->nres, c->stats, ncap, c->st);
     CK(cudaMemcpyAsync(c->h_stats, c->stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(c->ev1, c->st));
     if (wait_stream(c)) return WSPR_ERR_CUDA;
@@ -606,10 +638,9 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
         CK(cudaMemcpy(&overflow, &c->svc->queue->overflow, sizeof(int), cudaMemcpyDeviceToHost));
         if (overflow) return fail(WSPR_ERR_CUDA, "Fano queue overflow: parked candidates were lost");
     }
-    if (ht) {
-        if (hashtable_merge(c, *ht)) return WSPR_ERR_CUDA;
-        hashtable_write(*ht);
-    }
+    if (c->h_stats[3] > 0)
+        return fail(WSPR_ERR_LIMIT, "callsign hash list overflow: a capture produced more distinct hashed callsigns than HASH_CAP");
+    if (ht && hashtable_merge(c, *ht)) return WSPR_ERR_CUDA;
     for (size_t k = 0; k + 1 < kev_used; k += 2) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->kev[k], c->kev[k + 1]));
@@ -894,6 +925,23 @@ extern "C" void sync_and_demodulate(float *id, float *qd, long np, unsigned char
         if (v < -128) v = -128.0;
         symbols[i] = v + 128;
     }
+}
+
+// wsprd/wsprd.h:92-98 (exported by the reference, never called by it): the per-symbol subtraction
+extern "C" void subtract_signal(float *id, float *qd, long np, float f0, int shift, float drift, const unsigned char *channel_symbols) {
+    wspr_ctx *c = single_ctx((int)np);
+    int rc = c ? WSPR_OK : WSPR_ERR_CUDA;
+    if (!rc) rc = wspr_ctx_upload(c, id, qd, 1);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(c->caps, channel_symbols, NSYM, cudaMemcpyHostToDevice, c->st);   // (scratch use of the state buffer)
+        if (e == cudaSuccess) {
+            launch_subtract_symbolwise(c->I, c->Q, (int)np, f0, shift, drift, reinterpret_cast<const unsigned char *>(c->caps), c->st);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) rc = fail(WSPR_ERR_CUDA, "subtract_signal", e);
+    }
+    if (!rc) rc = wspr_ctx_download(c, nullptr, nullptr, id, qd);
+    if (rc) fprintf(stderr, "subtract_signal (libwsprd_b200): %s\n", g_err.c_str());
 }
 
 extern "C" void subtract_signal2(float *id, float *qd, long np, float f0, int shift, float drift,

@@ -820,75 +820,98 @@ __global__ void __launch_bounds__(SF_THREADS) k_sync_freqs_shared(const float *_
 }
 
 // soft symbols from the four tone magnitudes of one (frequency, lag) (:216-225,243-256) followed by the caller's
-// rms gate and the deinterleaver (:751-759).  Returns the mode-2 sync value.
-__device__ float soft_symbols(const float4 *__restrict__ p, unsigned char *sym_out, float *rms_out, int symfac) {
+// rms gate and the deinterleaver (:751-759).  Warp-cooperative: all 32 lanes call it; everything that is a per-symbol
+// expression runs across the lanes, every float accumulation of the reference (the two 162-term sync sums, the two moment
+// sums, the rms sum) is one lane adding in the reference's order.  `sync` is the metric ss/totp of these sums when the
+// caller already has it (the frequency search computes it), else it is computed here.  Returns the mode-2 sync value.
+struct SoftScratch {                                           // shared memory, one per calling warp
     float fs[NSYM];
+    float y2[NSYM];
+    unsigned char u8[NSYM + 2];
+    float bc[2];
+};
+__device__ float sync_metric(const float4 *__restrict__ p) {  // :216-218,227, one lane
     float ss = 0.0f, totp = 0.0f;
     for (int i = 0; i < NSYM; i++) {
         float4 q = p[i];
         totp = totp + q.x + q.y + q.z + q.w;
         float cmet = (q.y + q.w) - (q.x + q.z);
-        if (sync_bit(i)) {
-            ss = ss + cmet;
-            fs[i] = q.w - q.y;
-        } else {
-            ss = ss - cmet;
-            fs[i] = q.z - q.x;
+        ss = sync_bit(i) ? ss + cmet : ss - cmet;
+    }
+    return ss / totp;
+}
+__device__ float soft_symbols_warp(const float4 *__restrict__ p, unsigned char *sym_out, float *rms_out, int symfac,
+                                   bool have_sync, float sync, SoftScratch &sc) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (int i = lane; i < NSYM; i += 32) {
+        float4 q = p[i];
+        sc.fs[i] = sync_bit(i) ? q.w - q.y : q.z - q.x;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float ss = have_sync ? sync : sync_metric(p);
+        float syncmax = -1e30f;
+        if (ss > syncmax) syncmax = ss;
+        float fsum = 0.0f, f2sum = 0.0f;
+        for (int i = 0; i < NSYM; i++) {
+            const float f = sc.fs[i];
+            fsum += f / (float)NSYM;
+            f2sum += f * f / (float)NSYM;
         }
+        sc.bc[0] = __fsqrt_rn(f2sum - fsum * fsum);
+        sc.bc[1] = syncmax;
     }
-    ss = ss / totp;
-    float syncmax = -1e30f;
-    if (ss > syncmax) syncmax = ss;
-    float fsum = 0.0f, f2sum = 0.0f;
-    for (int i = 0; i < NSYM; i++) {
-        fsum += fs[i] / (float)NSYM;
-        f2sum += fs[i] * fs[i] / (float)NSYM;
-    }
-    float fac = __fsqrt_rn(f2sum - fsum * fsum);
-    unsigned char tmp[NSYM];
-    float sq = 0.0f;
-    for (int i = 0; i < NSYM; i++) {
-        float v = (float)symfac * fs[i] / fac;
+    __syncwarp();
+    const float fac = sc.bc[0];
+    for (int i = lane; i < NSYM; i += 32) {
+        float v = (float)symfac * sc.fs[i] / fac;
         if (v > 127.0f) v = 127.0f;
         if (v < -128.0f) v = -128.0f;
         float w = v + 128.0f;
         unsigned char u = (w >= 0.0f && w < 256.0f) ? (unsigned char)(int)w : (unsigned char)0;   // NaN -> 0 like cvttss2si's low byte
-        tmp[i] = u;
+        sc.u8[i] = u;
         float y = (float)((double)(float)u - 128.0);
-        sq += y * y;
+        sc.y2[i] = y * y;
     }
-    *rms_out = sqrtf(sq / (float)NSYM);
-    // deinterleave: p-th output is input at the p-th 8-bit-reversed index below 162 (wsprd_utils.c:196-213)
-    int pidx = 0;
-    for (int v = 0; pidx < NSYM; v++) {
-        int r = bitrev8(v);
-        if (r < NSYM) sym_out[pidx++] = tmp[r];
+    __syncwarp();
+    if (lane == 0) {
+        float sq = 0.0f;
+        for (int i = 0; i < NSYM; i++) sq += sc.y2[i];
+        *rms_out = sqrtf(sq / (float)NSYM);
     }
-    return syncmax;
+    // deinterleave: p-th output is input at the p-th 8-bit-reversed index below 162 (wsprd_utils.c:196-213); of the values
+    // v < 256 whose reversal is < 162, the ones below v are counted with a prefix over the warp
+    int base = 0;
+    for (int v0 = 0; v0 < 256; v0 += 32) {
+        const int v = v0 + (int)lane, r = bitrev8(v);
+        const unsigned m = __ballot_sync(0xffffffffu, r < NSYM);
+        if (r < NSYM) sym_out[base + __popc(m & ((1u << lane) - 1u))] = sc.u8[r];
+        base += __popc(m);
+    }
+    __syncwarp();
+    return sc.bc[1];
 }
 
 // arg-max over the five frequencies, the minsync1 gate, and the jitter-0 soft symbols, which are exactly the sums
-// of the winning hypothesis (mode 2 at the same frequency and lag repeats them) -- one thread per job
-__global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_list, int njobs,
-                            const float4 *__restrict__ P1, Attempt *__restrict__ att, float minsync1, float minrms,
-                            int symfac) {
-    int jx = blockIdx.x * blockDim.x + threadIdx.x;
+// of the winning hypothesis (mode 2 at the same frequency and lag repeats them) -- one warp per job: five lanes run the
+// five 162-term sync sums side by side
+constexpr int PICK_WARPS = 4;
+__global__ void __launch_bounds__(32 * PICK_WARPS) k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_list, int njobs,
+                                                               const float4 *__restrict__ P1, Attempt *__restrict__ att,
+                                                               float minsync1, float minrms, int symfac) {
+    __shared__ SoftScratch scratch[PICK_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jx = blockIdx.x * PICK_WARPS + warp;
     if (jx >= njobs) return;
     const int cap = job_list[jx];
     Job &job = jobs[cap];
     const float minsync2 = pass_minsync2(job.ipass);
+    float mine = 0.0f;
+    if (lane < NFREQ1) mine = sync_metric(P1 + ((size_t)jx * NFREQ1 + lane) * NSYM);
     float best = -1e30f, fbest = 0.0f;
     int bf = -1, bshift = 0;
     for (int fi = 0; fi < NFREQ1; fi++) {
-        const float4 *p = P1 + ((size_t)jx * NFREQ1 + fi) * NSYM;
-        float ss = 0.0f, totp = 0.0f;
-        for (int i = 0; i < NSYM; i++) {
-            float4 q = p[i];
-            totp = totp + q.x + q.y + q.z + q.w;
-            float cmet = (q.y + q.w) - (q.x + q.z);
-            ss = sync_bit(i) ? ss + cmet : ss - cmet;
-        }
-        ss = ss / totp;
+        const float ss = __shfl_sync(0xffffffffu, mine, fi);
         if (ss > best) {
             best = ss;
             bf = fi;
@@ -896,24 +919,28 @@ __global__ void k_pick_freq(Job *__restrict__ jobs, const int *__restrict__ job_
             bshift = job.shift;
         }
     }
+    const bool worth = best > minsync1;
     Attempt &a = att[cap];
-    a.cap = cap;
-    a.idt = 0;
-    a.gate = 0;
-    a.ok = 0;
-    a.unfinished = 0;
-    a.cycles = 0;
-    a.sync2 = 0.0f;
-    job.freq = fbest;
-    job.shift = bshift;
-    job.sync1 = best;
-    job.fbest = bf;
-    job.worth = best > minsync1;
-    if (job.worth && bf >= 0) {
-        float rms;
-        float s2 = soft_symbols(P1 + ((size_t)jx * NFREQ1 + bf) * NSYM, a.sym, &rms, symfac);
+    float s2 = 0.0f, rms = 0.0f;
+    if (worth && bf >= 0) {
+        float r = 0.0f;
+        s2 = soft_symbols_warp(P1 + ((size_t)jx * NFREQ1 + bf) * NSYM, a.sym, &r, symfac, true, best, scratch[warp]);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        rms = r;
+    }
+    if (lane == 0) {
+        a.cap = cap;
+        a.idt = 0;
+        a.ok = 0;
+        a.unfinished = 0;
+        a.cycles = 0;
         a.sync2 = s2;
-        a.gate = (s2 > minsync2) && (rms > minrms);
+        a.gate = (worth && bf >= 0) ? ((s2 > minsync2) && (rms > minrms)) : 0;
+        job.freq = fbest;
+        job.shift = bshift;
+        job.sync1 = best;
+        job.fbest = bf;
+        job.worth = worth;
     }
 }
 
@@ -926,7 +953,8 @@ void launch_sync_freqs(const float *I, const float *Q, Job *jobs, const int *job
     LAUNCHED();
     k_sync_freqs_shared<<<njobs, SF_THREADS, SF_SMEM_BYTES, st>>>(I, Q, jobs, job_list, P1, tabs, p.np, p.stride, PK_NEGZERO, PK_ONE);
     LAUNCHED();
-    k_pick_freq<<<(njobs + 63) / 64, 64, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms, p.symfac);
+    k_pick_freq<<<(njobs + PICK_WARPS - 1) / PICK_WARPS, 32 * PICK_WARPS, 0, st>>>(jobs, job_list, njobs, P1, att0, p.minsync1, p.minrms,
+                                                                                   p.symfac);
     LAUNCHED();
 }
 
@@ -1014,11 +1042,12 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
                                                      Job *__restrict__ jobs, const Attempt *__restrict__ att0,
                                                      CapState *__restrict__ caps, const int *__restrict__ defer_list,
-                                                     ChainScratch *__restrict__ scratch, int *__restrict__ stats,
-                                                     int *__restrict__ host_done, int nattempts, int np, int stride,
-                                                     float minrms, int symfac, pk2 negzero, pk2 one) {
+                                                     ChainScratch *__restrict__ scratch, const float4 *__restrict__ tabs,
+                                                     int *__restrict__ stats, int *__restrict__ host_done, int nattempts,
+                                                     int np, int stride, float minrms, int symfac, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float4 P[NSYM];
+    __shared__ SoftScratch soft;
     const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
     const int cap = defer_list[e];
     const Job &job = jobs[cap];
@@ -1042,8 +1071,10 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
     int ii = (idt + 1) / 2;
     if (idt % 2 == 1) ii = -ii;
     ii = 3 * ii;
+    // the phasor table of the job's final frequency is the one the frequency search of this round built for the winning
+    // hypothesis (same expression for the frequency, same recurrence): still in the round's table buffer
     const bool shared_tab = (job.drift == 0.0f);
-    if (shared_tab) build_tables(job.freq, tab, t);
+    if (shared_tab) load_tables(tab, tabs, job.slot, job.fbest, t, 192);
     __syncthreads();
     if (t < NSYM) {
         const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
@@ -1051,11 +1082,13 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
         P[t] = correlate_symbol(ip, qp, np, job.shift + ii + t * SPS, shared_tab, tab, fp, negzero, one);
     }
     __syncthreads();
-    if (t == 0) {
-        float rms;
-        const float s2 = soft_symbols(P, cs.sym[idt], &rms, symfac);
-        cs.gate[idt] = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
-        cs.ok[idt] = cs.unfinished[idt] = 0;
+    if (t < 32) {
+        float rms = 0.0f;
+        const float s2 = soft_symbols_warp(P, cs.sym[idt], &rms, symfac, false, 0.0f, soft);
+        if (t == 0) {
+            cs.gate[idt] = (s2 > pass_minsync2(job.ipass)) && (rms > minrms);
+            cs.ok[idt] = cs.unfinished[idt] = 0;
+        }
     }
 }
 
@@ -1225,11 +1258,12 @@ __global__ void __launch_bounds__(32) k_fano_workers(FanoQueue *__restrict__ q, 
 }
 
 void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p, cudaStream_t st) {
+                     ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
+                     cudaStream_t st) {
     if (n <= 0) return;
     const int nattempts = p.quickmode ? 1 : NJIT;
-    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, caps, defer_list, scratch, stats, host_done, nattempts, p.np,
-                                                      p.stride, p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
+    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, caps, defer_list, scratch, tabs, stats, host_done, nattempts,
+                                                      p.np, p.stride, p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
     LAUNCHED();
     k_fano_enqueue<<<1, 256, 0, st>>>(queue, scratch, defer_list, n);
     LAUNCHED();
@@ -1289,7 +1323,7 @@ __global__ void k_resolve(Job *__restrict__ jobs, CapState *__restrict__ caps, S
     const int cap = res_list[e];
     CapState &cs = caps[cap];
     cs.sub_pending = 0;
-    ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP, p.preload};
+    ListHashStore hs{cs.hash, &cs.nhash, HASH_CAP, p.preload, &cs.hash_overflow};
     const Job &job = jobs[cap];
     for (int once = 0; once < 1; once++) {                    // (the reference's `continue` / `break` targets)
         if (!(job.worth && job.decoded)) continue;
@@ -1390,42 +1424,68 @@ __global__ void k_sub_phase(const CapState *__restrict__ caps, const int *__rest
     }
 }
 
+// Four consecutive samples per thread, four symbols per CTA: the chain of dependent loads that every thread starts with
+// (list entry -> capture state -> recorded phase) and the rate set-up are paid once per four samples, and the four
+// sincos evaluations of a thread overlap.
+constexpr int SUBREF_SYMS = 4;                                 // symbols per CTA (64 threads each)
+constexpr int SUBREF_CTAS = (NSYM + SUBREF_SYMS - 1) / SUBREF_SYMS + 1;   // + one CTA that zeroes the pads of the product buffer
 __global__ void __launch_bounds__(SPS) k_sub_ref(const float *__restrict__ I, const float *__restrict__ Q,
                                                  const CapState *__restrict__ caps, const int *__restrict__ sublist,
                                                  const Counters *cnt, const float *__restrict__ phi_seg,
                                                  float2 *__restrict__ ref, float2 *__restrict__ cprod, int np, int stride) {
-    const int s = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
+    const int s = blockIdx.x, t = threadIdx.x;
     if (s >= cnt->nsub) return;
-    const int cap = sublist[s];
-    const CapState &cs = caps[cap];
-    if (i >= NSYM) {                    // extra CTAs zero the pads of the product buffer
+    if (blockIdx.y == SUBREF_CTAS - 1) {                       // pads: [0, 360) and [360 + NSIG, CPAD)
         float2 *c = cprod + (size_t)s * CPAD;
-        int z = (i - NSYM) * SPS + j;   // 0 .. 2*256-1 ; we need [0,360) and [360+NSIG, CPAD)
-        if (z < NFILT) c[z] = make_float2(0.0f, 0.0f);
-        int tailn = CPAD - (NFILT + NSIG);
-        if (z < tailn) c[NFILT + NSIG + z] = make_float2(0.0f, 0.0f);
+        constexpr int tailn = CPAD - (NFILT + NSIG);
+        for (int z = t; z < NFILT + tailn; z += SPS) c[z < NFILT ? z : NSIG + z] = make_float2(0.0f, 0.0f);
         return;
     }
-    const int ii = i * SPS + j, k = cs.sub_shift + ii;
+    const int i = blockIdx.y * SUBREF_SYMS + (t >> 6), j0 = (t & 63) * 4;
+    if (i >= NSYM) return;
+    const int cap = sublist[s];
+    const CapState &cs = caps[cap];
+    const int ii = i * SPS + j0, k0 = cs.sub_shift + ii;
     // the phase of sample ii: the recorded phase of its segment, then the reference's additions up to ii
     float phi = phi_seg[(size_t)s * (NSIG / PHI_SEG) + ii / PHI_SEG];
     const float dphi = sub_dphi(cs.sub_f0, cs.sub_drift, i, cs.chan[i]);
-    const int rem = j & (PHI_SEG - 1);
+    static_assert(PHI_SEG == 8, "a thread's four samples start at offset 0 or 4 of a recorded segment");
+    const bool second_half = (j0 & 4) != 0;
 #pragma unroll
-    for (int q = 0; q < PHI_SEG - 1; q++) {                  // (uniform instruction stream: lanes differ only in rem)
+    for (int q = 0; q < 4; q++) {                              // (uniform instruction stream: lanes differ only in the select)
         const float nxt = phi + dphi;
-        phi = (q < rem) ? nxt : phi;
+        phi = second_half ? nxt : phi;
     }
-    float rc, rs;
-    glibc_sincosf(phi, &rs, &rc);
-    float2 c = make_float2(0.0f, 0.0f);
-    if (k > 0 && k < np) {               // :375-381
-        float x = I[(size_t)cap * stride + k], y = Q[(size_t)cap * stride + k];
-        c.x = x * rc + y * rs;
-        c.y = y * rc - x * rs;
+    const float *ip = I + (size_t)cap * stride, *qp = Q + (size_t)cap * stride;
+    float xs[4], ys[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int k = k0 + u;
+        const bool in = k > 0 && k < np;                       // :375-381
+        xs[u] = in ? ip[k] : 0.0f;
+        ys[u] = in ? qp[k] : 0.0f;
     }
-    ref[(size_t)s * NSIG + ii] = make_float2(rc, rs);
-    cprod[(size_t)s * CPAD + NFILT + ii] = c;
+    float2 r4[4], c4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        float rc, rs;
+        glibc_sincosf(phi, &rs, &rc);
+        phi = phi + dphi;
+        const int k = k0 + u;
+        float2 c = make_float2(0.0f, 0.0f);
+        if (k > 0 && k < np) {
+            c.x = xs[u] * rc + ys[u] * rs;
+            c.y = ys[u] * rc - xs[u] * rs;
+        }
+        r4[u] = make_float2(rc, rs);
+        c4[u] = c;
+    }
+    float4 *rp = reinterpret_cast<float4 *>(ref + (size_t)s * NSIG + ii);
+    float4 *cp = reinterpret_cast<float4 *>(cprod + (size_t)s * CPAD + NFILT + ii);
+    rp[0] = make_float4(r4[0].x, r4[0].y, r4[1].x, r4[1].y);
+    rp[1] = make_float4(r4[2].x, r4[2].y, r4[3].x, r4[3].y);
+    cp[0] = make_float4(c4[0].x, c4[0].y, c4[1].x, c4[1].y);
+    cp[1] = make_float4(c4[2].x, c4[2].y, c4[3].x, c4[3].y);
 }
 
 constexpr int LPF_R = 4;                                     // consecutive outputs per thread
@@ -1509,7 +1569,7 @@ void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublis
     if (nsub_max <= 0) return;
     k_sub_phase<<<(nsub_max + 31) / 32, 32, 0, st>>>(caps, sublist, cnt, phi0);
     LAUNCHED();
-    k_sub_ref<<<dim3(nsub_max, NSYM + 2), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
+    k_sub_ref<<<dim3(nsub_max, SUBREF_CTAS), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
     constexpr int T = WSPR_LPF_THREADS;
     k_sub_lpf<T><<<dim3(nsub_max, (NSIG + 4 * T - 1) / (4 * T)), T, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np, p.stride,
@@ -1532,6 +1592,7 @@ __global__ void k_reset_caps(CapState *caps, int ncap, int npasses) {
     cs.broken = 0;
     cs.nhash = 0;
     cs.sub_pending = 0;
+    cs.hash_overflow = 0;
 }
 void launch_reset_caps(CapState *caps, int ncap, int npasses, cudaStream_t st) {
     if (ncap <= 0) return;
@@ -1540,9 +1601,11 @@ void launch_reset_caps(CapState *caps, int ncap, int npasses, cudaStream_t st) {
 }
 
 // final stable sort by SNR, descending (wsprd.c:827) and the spot count
-__global__ void k_finish(CapState *__restrict__ caps, Spot *__restrict__ spots, int *__restrict__ nres, int ncap) {
+__global__ void k_finish(CapState *__restrict__ caps, Spot *__restrict__ spots, int *__restrict__ nres, int *__restrict__ stats,
+                         int ncap) {
     int cap = blockIdx.x * blockDim.x + threadIdx.x;
     if (cap >= ncap) return;
+    if (caps[cap].hash_overflow) atomicAdd(stats + 3, 1);
     Spot *r = spots + (size_t)cap * MAXUNIQ;
     int n = caps[cap].uniques;
     for (int i = 1; i < n; i++) {
@@ -1556,9 +1619,9 @@ __global__ void k_finish(CapState *__restrict__ caps, Spot *__restrict__ spots, 
     }
     nres[cap] = n;
 }
-void launch_finish(CapState *caps, Spot *spots, int *nres, int ncap, cudaStream_t st) {
+void launch_finish(CapState *caps, Spot *spots, int *nres, int *stats, int ncap, cudaStream_t st) {
     if (ncap <= 0) return;
-    k_finish<<<(ncap + 31) / 32, 32, 0, st>>>(caps, spots, nres, ncap);
+    k_finish<<<(ncap + 31) / 32, 32, 0, st>>>(caps, spots, nres, stats, ncap);
     LAUNCHED();
 }
 
@@ -1612,6 +1675,48 @@ void launch_sync_generic(const float *I, const float *Q, int np, float freq, int
     int nf = ifmax - ifmin + 1, nl = (lagmax - lagmin) / lagstep + 1;
     if (nf <= 0 || nl <= 0) return;
     k_sync_generic<<<dim3(nl, nf), 192, 0, st>>>(I, Q, np, freq, ifmin, fstep, lagmin, lagstep, drift, P, PK_NEGZERO, PK_ONE);
+    LAUNCHED();
+}
+
+// =========================================================================================================
+// subtract_signal (wsprd.c:263-312): the per-symbol variant the reference exports but never calls.  One thread per symbol
+// (the symbols touch disjoint samples): phasor recurrence, the two 256-term sums in sample order, subtraction.
+// =========================================================================================================
+__global__ void __launch_bounds__(192) k_sub_symbolwise(float *__restrict__ I, float *__restrict__ Q, int np, float f0, int shift,
+                                                        float drift, const unsigned char *__restrict__ chan) {
+    const int i = threadIdx.x;
+    if (i >= NSYM) return;
+    const float fp = symbol_freq(f0, drift, i);                                             // :274
+    const float dphi = (float)(twopidt() * ((double)fp + ((double)(float)chan[i] - 1.5) * 375.0 / 256.0));   // :276
+    const float cd = glibc_cosf(dphi), sd = glibc_sinf(dphi);
+    float i0 = 0.0f, q0 = 0.0f, c = 1.0f, s = 0.0f;
+    for (int j = 0; j < SPS; j++) {
+        const int k = shift + i * SPS + j;
+        if (k > 0 && k < np) {
+            i0 = i0 + I[k] * c + Q[k] * s;
+            q0 = q0 - I[k] * s + Q[k] * c;
+        }
+        const float cn = c * cd - s * sd, sn = c * sd + s * cd;
+        c = cn;
+        s = sn;
+    }
+    i0 = i0 / (float)SPS;
+    q0 = q0 / (float)SPS;
+    c = 1.0f;
+    s = 0.0f;
+    for (int j = 0; j < SPS; j++) {
+        const int k = shift + i * SPS + j;
+        if (k > 0 && k < np) {
+            I[k] = I[k] - (i0 * c - q0 * s);
+            Q[k] = Q[k] - (q0 * c + i0 * s);
+        }
+        const float cn = c * cd - s * sd, sn = c * sd + s * cd;
+        c = cn;
+        s = sn;
+    }
+}
+void launch_subtract_symbolwise(float *I, float *Q, int np, float f0, int shift, float drift, const unsigned char *chan, cudaStream_t st) {
+    k_sub_symbolwise<<<1, 192, 0, st>>>(I, Q, np, f0, shift, drift, chan);
     LAUNCHED();
 }
 

@@ -109,6 +109,7 @@ struct CapState {
     int broken;         // the reference hit one of its `break`s in this pass
     int nhash;
     int sub_pending;    // a subtraction has been scheduled by the resolve step
+    int hash_overflow;  // more than HASH_CAP distinct callsign hashes in one capture: an entry was dropped
     float sub_f0, sub_drift;
     int sub_shift;
     float allfreqs[MAXUNIQ];
@@ -196,7 +197,8 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 // n candidates into the device queue; launch_fano_workers starts up to `nwarps` worker warps on `st` (they leave at once
 // when the pool is already complete, and when the queue runs dry)
 void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p, cudaStream_t st);
+                     ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
+                     cudaStream_t st);
 void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st);
 void init_kernel_attributes();               // per device: opt-in to > 48 KB of dynamic shared memory
 int fano_warp_smem_bytes();                  // shared memory one worker warp holds
@@ -204,7 +206,9 @@ void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list,
                     const DecodeParams &p, cudaStream_t st);
 void launch_subtract(float *I, float *Q, const CapState *caps, const int *sub_list, int nsub_max, const Counters *cnt,
                      float *phi0, float2 *ref, float2 *cprod, const DecodeParams &p, cudaStream_t st);
-void launch_finish(CapState *caps, Spot *spots, int *nres, int ncap, cudaStream_t st);
+void launch_finish(CapState *caps, Spot *spots, int *nres, int *stats, int ncap, cudaStream_t st);
+// stand-alone per-symbol subtraction (subtract_signal, wsprd.c:263-312) on one capture resident on the device
+void launch_subtract_symbolwise(float *I, float *Q, int np, float f0, int shift, float drift, const unsigned char *chan, cudaStream_t st);
 void launch_normalise(float *I, float *Q, int ncap, int n, int stride, cudaStream_t st);
 
 // stand-alone single-call forms used by the reference-ABI wrappers (sync_and_demodulate / subtract_signal2)

@@ -522,3 +522,49 @@ def write_iq_file(path, i, q):
     buf[1::2] = -np.asarray(q, np.float32)
     buf.tofile(path)
     return len(i)
+
+
+def load_capture_files(paths, nmax=NSAMP, pinned=False):
+    """Batch loader for the on-disk formats either side of the path: a directory or a list of `.iq` / `.c2`
+    recordings -> the planar [n][45000] float32 batch that BatchDecoder.upload takes.  Every file goes through the
+    reference's own reader semantics (readRawIQfile / readC2file, rtlsdr_wsprd.c:555-667: Q negated, peak-normalised to
+    0.5); short recordings are zero-padded like the daemon's hand-off (rtlsdr_wsprd.c:285-288).
+    Returns (I, Q, dialfreq[n] (0 for .iq files), names).  pinned=True puts I and Q in page-locked memory (torch), so that
+    the upload is an asynchronous DMA."""
+    if isinstance(paths, (str, os.PathLike)):
+        root = os.fspath(paths)
+        if os.path.isdir(root):
+            paths = sorted(os.path.join(root, f) for f in os.listdir(root) if f.lower().endswith((".iq", ".c2")))
+        else:
+            paths = [root]
+    paths = [os.fspath(x) for x in paths]
+    n = len(paths)
+    if pinned:
+        import torch
+        ti = torch.zeros((n, nmax), dtype=torch.float32).pin_memory()
+        tq = torch.zeros((n, nmax), dtype=torch.float32).pin_memory()
+        I, Q = ti.numpy(), tq.numpy()
+    else:
+        I, Q = np.zeros((n, nmax), np.float32), np.zeros((n, nmax), np.float32)
+    freq = np.zeros(n, np.float64)
+    for k, path in enumerate(paths):
+        if path.lower().endswith(".c2"):
+            i, q, freq[k] = read_c2_file(path, nmax)
+        else:
+            i, q = read_iq_file(path, nmax)
+        I[k, : len(i)], Q[k, : len(q)] = i, q
+    return I, Q, freq, [os.path.basename(x) for x in paths]
+
+
+def write_c2_file(path, i, q, dialfreq, name=b"000000_0000.c2", ftype=2):
+    """The .c2 layout readC2file expects (rtlsdr_wsprd.c:619-640): 14-byte name, int type, double dial frequency, then
+    interleaved f32 (I, -Q)."""
+    buf = np.empty(2 * len(i), "<f4")
+    buf[0::2] = i
+    buf[1::2] = -np.asarray(q, np.float32)
+    with open(path, "wb") as f:
+        f.write(bytes(name)[:14].ljust(14, b"\0"))
+        f.write(struct.pack("<i", int(ftype)))
+        f.write(struct.pack("<d", float(dialfreq)))
+        buf.tofile(f)
+    return len(i)

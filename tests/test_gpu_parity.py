@@ -471,3 +471,100 @@ def test_streaming_frontend_against_reference_callback_and_decoder_hand_off():
     a, b = I[0].copy(), Q[0].copy()
     po.oracle().oracle_normalise(a.ctypes.data_as(FP), b.ctypes.data_as(FP), a.shape[0])
     assert np.array_equal(Id[0], a) and np.array_equal(Qd[0], b)
+
+
+def test_subtract_signal_abi_against_compiled_reference():
+    """subtract_signal (wsprd/wsprd.h:92-98, the per-symbol variant the reference exports but never calls) through the C ABI
+    against the reference's own object code (oracle/_ref travels to the GPU box prebuilt), with and without drift."""
+    ref = po.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/libwsprd_ref.so not available")
+    ref.subtract_signal.restype = None
+    ref.subtract_signal.argtypes = [FP, FP, C.c_long, C.c_float, C.c_int, C.c_float, UP]
+    lib = w.library()
+    lib.subtract_signal.restype = None
+    lib.subtract_signal.argtypes = [FP, FP, C.c_long, C.c_float, C.c_int, C.c_float, UP]
+    I, Q, plans = H.make_corpus(3, 1, start=77)
+    for k, (f0, shift, drift) in enumerate([(plans[0][3]["f0"], 760, 0.0), (-41.7, 3, -1.0), (12.3, 4000, 2.0), (99.0, -30, 0.0)]):
+        chan = H.channel_symbols(plans[0][k]["message"])
+        ia, qa, ib, qb = I[0].copy(), Q[0].copy(), I[0].copy(), Q[0].copy()
+        ref.subtract_signal(ia.ctypes.data_as(FP), qa.ctypes.data_as(FP), 45000, C.c_float(f0), shift, C.c_float(drift), chan.ctypes.data_as(UP))
+        lib.subtract_signal(ib.ctypes.data_as(FP), qb.ctypes.data_as(FP), 45000, C.c_float(f0), shift, C.c_float(drift), chan.ctypes.data_as(UP))
+        assert not np.array_equal(ia, I[0])
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb), (k, np.abs(ia - ib).max())
+
+
+def test_four_passes_keep_pass_two_parameters():
+    """npasses >= 4: passes 3.. keep maxdrift = 0 / minsync2 = 0.10 of pass 2 (wsprd.c:524-531 only assign for ipass < 2 and == 2)."""
+    I, Q, _ = H.make_corpus(3, 4, start=2100, )
+    opt_o, opt_g = po.default_options(npasses=4), w.default_options(npasses=4)
+    got = w.decode_batch(I, Q, opt_g)
+    for c in range(len(I)):
+        a, _, _ = po.decode(po.ref() or po.oracle(), I[c], Q[c], opt_o)
+        assert H.results_equal(a, got[c]), (c, H.diff_results(a, got[c]))
+
+
+def test_two_devices_in_one_process():
+    """Contexts on two GPUs of one process (kernel attributes and the Fano service are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    I, Q, _ = H.make_corpus(3, 6, start=2200)
+    want = [po.decode(po.oracle(), I[c], Q[c])[0] for c in range(len(I))]
+    with w.BatchDecoder(6, device=0) as d0, w.BatchDecoder(6, device=1) as d1:
+        for d in (d1, d0, d1):
+            d.upload(I, Q)
+            d.decode()
+            spots, n = d.download()
+            for c in range(len(I)):
+                assert H.results_equal(want[c], spots[c, : n[c]]), (d.device, c)
+
+
+def test_hashtable_batch_versus_capture_by_capture():
+    """-H with several captures in ONE call: every capture sees hashtable.txt as it was on entry and the additions are merged
+    in capture order.  The reference's call-by-call order differs exactly where a capture refers by hash to a callsign that
+    an EARLIER capture of the same batch taught: the batch leaves <...> there, the sequential run resolves it.  Everything
+    else -- and the file left behind -- is identical."""
+    import tempfile
+    caps = H.hashtable_scenario()                      # A teaches, B refers by hash, A again
+    I, Q = np.stack([c[0] for c in caps]), np.stack([c[1] for c in caps])
+    opt_o, opt_g = po.default_options(usehashtable=1), w.default_options(usehashtable=1)
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory(prefix="wspr_htb_") as d:
+        os.chdir(d)
+        try:
+            seq = [po.decode(po.oracle(), I[c], Q[c], opt_o, cwd_scratch=False)[0] for c in range(3)]
+            seq_file = open("hashtable.txt").read()
+            os.remove("hashtable.txt")
+            got = w.decode_batch(I, Q, opt_g)
+            batch_file = open("hashtable.txt").read()
+            again = w.decode_batch(I, Q, opt_g)        # second call: the table of the first is on disk now
+        finally:
+            os.chdir(old)
+    assert batch_file == seq_file
+    assert H.results_equal(seq[0], got[0]) and H.results_equal(seq[2], got[2])
+    unresolved = [x["message"] for x in got[1] if b"<...>" in x["message"]]
+    resolved = [x["message"] for x in seq[1] if x["message"].startswith(b"<") and b"<...>" not in x["message"]]
+    assert len(unresolved) >= len(resolved) >= 2 and len(got[1]) == len(seq[1])
+    assert H.results_equal(seq[1], again[1])           # with the table on disk the batch resolves them like the reference
+
+
+def test_sharded_decode_on_two_gpus(tmp_path):
+    """sharding.decode_sharded with the real decoder, one process per GPU over NCCL (launched like the driver launches
+    bench.py), against the oracle."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    out = str(tmp_path / "sharded.npz")
+    script = os.path.join(H.ROOT, "tests", "sharded_worker.py")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29611", script, out, "7"], check=True, timeout=600)
+    z = np.load(out)
+    spots, n = z["spots"].view(w.RESULT_DTYPE).reshape(-1, w.MAX_UNIQUES), z["n"]
+    I, Q, _ = H.make_corpus(3, 7, start=2300)
+    assert len(n) == 7
+    for c in range(7):
+        a, _, _ = po.decode(po.oracle(), I[c], Q[c])
+        assert H.results_equal(a, spots[c, : n[c]]), (c, H.diff_results(a, spots[c, : n[c]]))

@@ -76,3 +76,26 @@ def test_corpus_is_seeded_and_counter_based():
     assert a[2][1] == b[2][0] and len(a[2][0]) == 10
     snrs = sorted(s["snr"] for s in a[2][0])
     assert snrs == list(np.arange(-28.0, -9.0, 2.0))
+
+
+def test_batch_file_loader(tmp_path):
+    """N2: a directory of .iq / .c2 recordings -> the planar [n][45000] batch, every file through the reference's reader
+    semantics (Q negated, peak-normalised, short files zero-padded)."""
+    I, Q, _ = H.make_corpus(2, 3)
+    w.write_iq_file(str(tmp_path / "b.iq"), I[0], Q[0])
+    w.write_c2_file(str(tmp_path / "a.c2"), I[1], Q[1], 7.0386)
+    w.write_iq_file(str(tmp_path / "c.iq"), I[2][:30000], Q[2][:30000])
+    (tmp_path / "notes.txt").write_text("ignored")
+    bi, bq, freq, names = w.load_capture_files(str(tmp_path))
+    assert names == ["a.c2", "b.iq", "c.iq"] and bi.shape == (3, 45000) and bi.dtype == np.float32
+    assert freq.tolist() == [7.0386, 0.0, 0.0]
+    for k, src in enumerate((1, 0)):
+        ni, nq = w.normalise_half(I[src], Q[src])
+        assert np.array_equal(bi[k], ni) and np.array_equal(bq[k], nq)
+    si, sq = w.normalise_half(I[2][:30000], Q[2][:30000])
+    assert np.array_equal(bi[2, :30000], si) and np.array_equal(bq[2, :30000], sq) and not bi[2, 30000:].any() and not bq[2, 30000:].any()
+    # a list of paths, and the reference's own fixture through the loader and the oracle-side reader
+    fix = os.path.join(H.GOLDEN, "refSignalSnr0dB.iq")
+    li, lq, _, _ = w.load_capture_files([fix, str(tmp_path / "b.iq")])
+    ri, rq = po.read_iq_file(fix)
+    assert np.array_equal(li[0], ri) and np.array_equal(lq[0], rq) and np.array_equal(li[1], bi[1])
