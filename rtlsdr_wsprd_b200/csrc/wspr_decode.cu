@@ -80,9 +80,16 @@ static void host_tables(HostTables &t) {
 //   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
 //                   per SM unpartitioned)
 //   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
+//   WSPR_CARVEOUT_KB  common shared-memory carve-out of every decode kernel (0 = the driver's per-kernel choice)
 // All are read once, when the first context on a device is created.
 #ifndef WSPR_DEFAULT_FANO_SMS
 #define WSPR_DEFAULT_FANO_SMS 0
+#endif
+#ifndef WSPR_DEFAULT_CARVEOUT_KB
+#define WSPR_DEFAULT_CARVEOUT_KB 164              // K4's two 47 KB CTAs + two worker warps; measured in profiles/r2_bench_variants.txt
+#endif
+#ifndef WSPR_DEFAULT_FANO_PER_SM
+#define WSPR_DEFAULT_FANO_PER_SM 2
 #endif
 #ifndef WSPR_DEFAULT_FANO_POOL_PER_SM
 #define WSPR_DEFAULT_FANO_POOL_PER_SM 2
@@ -150,7 +157,7 @@ static FanoService *fano_service(int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return nullptr; }
     s->total_sms = prop.multiProcessorCount;
-    init_kernel_attributes();
+    init_kernel_attributes(env_int("WSPR_CARVEOUT_KB", WSPR_DEFAULT_CARVEOUT_KB));
     const int want = env_int("WSPR_FANO_SMS", WSPR_DEFAULT_FANO_SMS);
     if (want > 0 && want < s->total_sms) {
         s->partitioned = fano_partition(s, want);
@@ -163,7 +170,7 @@ static FanoService *fano_service(int device) {
     FanoQueue h;
     memset(&h, 0, sizeof h);
     h.pool = s->pool;
-    h.per_sm = env_int("WSPR_FANO_PER_SM", 0);
+    h.per_sm = env_int("WSPR_FANO_PER_SM", s->partitioned ? 0 : WSPR_DEFAULT_FANO_PER_SM);
     h.mask = FANO_RING - 1;
     if (cudaMalloc((void **)&s->ring, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||
         cudaMemset(s->ring, 0, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||

@@ -6,6 +6,7 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -1272,7 +1273,14 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *a
 int fano_warp_smem_bytes() { return FANO_WARP_SMEM_BYTES; }
 void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st) {
     if (nwarps <= 0) return;
-    k_fano_workers<<<nwarps, 32, FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta, p.maxcycles);
+    unsigned maxcycles = p.maxcycles;
+#ifdef WSPR_EXPERIMENTS
+    // experiment builds only (make exp -> libwsprd_b200_exp.so): cut the long Fano runs short -- WRONG results -- to measure
+    // what the bulk of the decode costs without them
+    static const unsigned dbg = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
+    if (dbg) maxcycles = dbg;
+#endif
+    k_fano_workers<<<nwarps, 32, FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta, maxcycles);
     LAUNCHED();
 }
 
@@ -1722,8 +1730,22 @@ void launch_subtract_symbolwise(float *I, float *Q, int np, float f0, int shift,
 
 // Opt in to > 48 KB of dynamic shared memory (k_sync_freqs_shared).  Function attributes belong to the device that is
 // current, so this runs once per device (wspr_decode.cu calls it when it sets a device up).
-void init_kernel_attributes() {
+// carveout_kb > 0: every decode kernel asks for the SAME shared-memory carve-out.  An SM cannot change its L1/shared split
+// while a CTA is resident, and the Fano worker warps are resident practically all the time: with the driver's per-kernel
+// choice an SM stays frozen at whatever split it had when a worker landed on it, and kernels that need more shared memory
+// than that split leaves (K4: 2 x 47 KB) can only use the SM partly or not at all.  With one common split nothing ever has
+// to wait for an SM to drain.
+void init_kernel_attributes(int carveout_kb) {
     cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
+    if (carveout_kb <= 0) return;
+    const int pct = std::min(100, (carveout_kb * 100 + 227) / 228);
+#define WSPR_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct)
+    WSPR_CARVE(k_spectrogram); WSPR_CARVE(k_candidates); WSPR_CARVE(k_coarse); WSPR_CARVE(k_setup_done); WSPR_CARVE(k_plan);
+    WSPR_CARVE(k_tables); WSPR_CARVE(k_sync_lags); WSPR_CARVE(k_pick_lag); WSPR_CARVE(k_sync_freqs); WSPR_CARVE(k_sync_freqs_shared);
+    WSPR_CARVE(k_pick_freq); WSPR_CARVE(k_fano_round); WSPR_CARVE(k_collect); WSPR_CARVE(k_jitter_soft); WSPR_CARVE(k_fano_enqueue);
+    WSPR_CARVE(k_fano_workers); WSPR_CARVE(k_resolve); WSPR_CARVE(k_sub_phase); WSPR_CARVE(k_sub_ref);
+    WSPR_CARVE(k_sub_lpf<WSPR_LPF_THREADS>); WSPR_CARVE(k_reset_caps); WSPR_CARVE(k_finish); WSPR_CARVE(k_normalise);
+#undef WSPR_CARVE
 }
 
 }  // namespace wspr

@@ -200,7 +200,7 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *a
                      ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
                      cudaStream_t st);
 void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st);
-void init_kernel_attributes();               // per device: opt-in to > 48 KB of dynamic shared memory
+void init_kernel_attributes(int carveout_kb);   // per device: opt-in to > 48 KB of dynamic shared memory, common carve-out
 int fano_warp_smem_bytes();                  // shared memory one worker warp holds
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,
                     const DecodeParams &p, cudaStream_t st);
