@@ -113,6 +113,11 @@ const char *wspr_last_error(void);
 int wspr_ctx_upload(wspr_ctx *ctx, const float *I, const float *Q, int ncaptures);
 /* use captures already resident in device memory (device pointers, row stride in floats); copied device-to-device */
 int wspr_ctx_upload_device(wspr_ctx *ctx, const float *dI, const float *dQ, int ncaptures, int row_stride);
+/* raw 2.4 Msps u8 IQ streams resident on the device -> the context's sample planes: rtlsdr_callback (rtlsdr_wsprd.c:126-244)
+ * for nstreams whole streams of n_iq samples (16-byte aligned, stream_stride_bytes apart), tail zeroed like the hand-off
+ * (rtlsdr_wsprd.c:285-288).  Asynchronous on the context's stream; follow with wspr_ctx_normalise and wspr_ctx_decode.
+ * Returns the samples each stream produced (n_iq / 6401, at most the context's capture length). */
+int wspr_ctx_decimate(wspr_ctx *ctx, const uint8_t *d_raw, int nstreams, size_t n_iq, size_t stream_stride_bytes);
 /* peak-normalise every resident capture to 0.5 (rtlsdr_wsprd.c:291-305) */
 int wspr_ctx_normalise(wspr_ctx *ctx);
 /* decode the resident captures (both passes, subtraction, ...); results stay on the device until downloaded */

@@ -80,6 +80,7 @@ static void host_tables(HostTables &t) {
 //   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
 //                   per SM unpartitioned)
 //   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
+//   WSPR_FANO_CTA_WARPS  worker warps per CTA (1, 2 or 4)
 //   WSPR_CARVEOUT_KB  common shared-memory carve-out of every decode kernel (0 = the driver's per-kernel choice)
 // All are read once, when the first context on a device is created.
 #ifndef WSPR_DEFAULT_FANO_SMS
@@ -87,6 +88,9 @@ static void host_tables(HostTables &t) {
 #endif
 #ifndef WSPR_DEFAULT_CARVEOUT_KB
 #define WSPR_DEFAULT_CARVEOUT_KB 164              // K4's two 47 KB CTAs + two worker warps; measured in profiles/r2_bench_variants.txt
+#endif
+#ifndef WSPR_DEFAULT_FANO_CTA_WARPS
+#define WSPR_DEFAULT_FANO_CTA_WARPS 1
 #endif
 #ifndef WSPR_DEFAULT_FANO_PER_SM
 #define WSPR_DEFAULT_FANO_PER_SM 2
@@ -99,7 +103,7 @@ constexpr int NFANO_STREAMS = 4;
 
 struct FanoService {
     int device = -1;
-    int fano_sms = 0, pool = 0, total_sms = 0;
+    int fano_sms = 0, pool = 0, total_sms = 0, cta_warps = 1;
     bool partitioned = false;
     CUgreenCtx g_fano = nullptr, g_bulk = nullptr;
     FanoQueue *queue = nullptr;                    // device
@@ -167,6 +171,7 @@ static FanoService *fano_service(int device) {
     const int per_sm = (228 * 1024) / (fano_warp_smem_bytes() + 1024);
     s->pool = env_int("WSPR_FANO_POOL", s->partitioned ? s->fano_sms * per_sm : s->total_sms * WSPR_DEFAULT_FANO_POOL_PER_SM);
     if (s->pool < 1) s->pool = 1;
+    s->cta_warps = env_int("WSPR_FANO_CTA_WARPS", WSPR_DEFAULT_FANO_CTA_WARPS);
     FanoQueue h;
     memset(&h, 0, sizeof h);
     h.pool = s->pool;
@@ -233,6 +238,8 @@ struct wspr_ctx {
     float2 *ref = nullptr, *cprod = nullptr;
     Counters *cnt = nullptr;       // device
     Counters *h_cnt = nullptr;     // pinned host mirror
+    uint4 *moments = nullptr;      // front-end scratch of wspr_ctx_decimate: [streams][blocks] block moments
+    size_t moments_cap = 0;
     ChainScratch *scratch = nullptr;   // [maxcap], leased from the service
     int *h_done = nullptr;         // pinned, device-visible: parked captures handed back by the Fano workers so far
     char *preload = nullptr;       // device [32768][13]: hashtable.txt calls (allocated on the first -H decode)
@@ -258,7 +265,7 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     cudaDeviceSynchronize();
     void *ptrs[] = {c->I, c->Q, c->psT, c->smspec, c->cands, c->caps, c->spots, c->nres, c->jobs, c->att0, c->ident,
                     c->setup_list, c->job_list, c->res_list, c->sub_list, c->defer_list, c->P0, c->P1, c->tabs, c->phi0, c->ref, c->cprod,
-                    c->cnt, c->stats, c->preload};
+                    c->cnt, c->stats, c->preload, c->moments};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->scratch && c->svc) {
@@ -379,6 +386,31 @@ extern "C" int wspr_ctx_upload_device(wspr_ctx *c, const float *dI, const float 
     CK(cudaMemcpy2DAsync(c->Q, (size_t)c->stride * sizeof(float), dQ, (size_t)row_stride * sizeof(float), w, ncap,
                          cudaMemcpyDeviceToDevice, c->st));
     return WSPR_OK;
+}
+
+// Raw streams straight into the context (BASELINE config 4): rtlsdr_callback (rtlsdr_wsprd.c:126-244) for `nstreams` whole
+// streams resident on the device, written into the context's sample planes with the tail zeroed like the daemon's hand-off
+// (rtlsdr_wsprd.c:285-288); follow with wspr_ctx_normalise (:291-305) and wspr_ctx_decode (:316).  Asynchronous on the
+// context's stream.  Returns the samples every stream produced, or a negative error.
+extern "C" int wspr_ctx_decimate(wspr_ctx *c, const uint8_t *d_raw, int nstreams, size_t n_iq, size_t stream_stride_bytes) {
+    if (!c || !d_raw || nstreams < 0 || nstreams > c->maxcap) return fail(WSPR_ERR_ARG, "wspr_ctx_decimate: bad arguments");
+    if (((uintptr_t)d_raw & 15) || (stream_stride_bytes & 15) || stream_stride_bytes < 2 * n_iq)
+        return fail(WSPR_ERR_ARG, "wspr_ctx_decimate: raw streams must be 16-byte aligned and strided");
+    CK(cudaSetDevice(c->device));
+    c->ncap = nstreams;
+    if (nstreams == 0) return 0;
+    const int nblk = decimate_outputs(n_iq);
+    const size_t need = (size_t)nstreams * (size_t)std::max(nblk, 1);
+    if (c->moments_cap < need) {
+        if (c->moments) CK(cudaFree(c->moments));
+        c->moments = nullptr;
+        c->moments_cap = 0;
+        CK(dalloc(&c->moments, need));
+        c->moments_cap = need;
+    }
+    launch_decimate(d_raw, n_iq, nstreams, stream_stride_bytes, c->moments, c->I, c->Q, c->stride, c->np, c->st);
+    CK(cudaGetLastError());
+    return std::min(nblk, c->np);
 }
 
 extern "C" int wspr_ctx_normalise(wspr_ctx *c) {
@@ -626,7 +658,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];
                 CK(cudaStreamWaitEvent(fs, c->ev_fano, 0));
                 const int attempts = ndefer * (p.quickmode ? 1 : NJIT);
-                launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), p, fs);
+                launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), c->svc->cta_warps, p, fs);
             }
         }
         // in-order tail of the candidate loop for everything that finished, then the subtractions (wsprd.c:768-822)

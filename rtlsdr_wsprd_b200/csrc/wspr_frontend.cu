@@ -49,68 +49,54 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {        // read-once
     return v;
 }
 
-// Mixer weights.  A 16-byte vector holds samples n = 8V .. 8V+7 as bytes (I0 Q0 I1 Q1 | I2 Q2 I3 Q3 | ...), and
-// 8V = 0 mod 4, so word 0/2 holds mixer phases 0,1 and word 1/3 phases 2,3:
+// Mixer.  A 16-byte vector holds samples n = 8V .. 8V+7 as bytes (I0 Q0 I1 Q1 | I2 Q2 I3 Q3 | ...), and 8V = 0 mod 4, so
+// word 0/2 holds mixer phases 0,1 and word 1/3 phases 2,3:
 //   phase 0: (I,Q) ; 1: (-Q, I) ; 2: (-I,-Q) ; 3: (Q,-I)                       (rtlsdr_wsprd.c:171-182)
-// Bytes are used offset-binary (u = s + 128); the -128*sum(weights) term vanishes because every weight vector
-// below sums to zero over a whole vector only for the cross terms -- it is therefore removed explicitly: each
-// accumulated sum is corrected by 128 * (sum of the weights applied), which is tracked in closed form (all
-// weights of one channel over one vector cancel: +1 -1 -1 +1), except that masked (out-of-block) bytes are
-// replaced by 128 so that they contribute s = 0.
-// The reference negates in int8, so -(-128) stays -128: a negated byte with u == 0 contributes 256 less than
-// the linear sum.  Vectors containing a zero byte take a per-byte correction path.
+// The reference negates in int8, so -(-128) stays -128.  In the offset-binary form the bytes arrive in (u = s + 128) that
+// wrap-around is exactly the negation of the BYTE modulo 256: u' = (-u) & 255 (u = 0 -> 0, i.e. s = -128 -> -128).  So the
+// bytes at the negated positions -- byte 3 of words 0/2 (phase 1: -Q), bytes 0,1,2 of words 1/3 (phase 2: -I, -Q; phase 3:
+// -I) -- are negated byte-wise (carry-free SWAR), after which EVERY word holds the mixer outputs in the same places:
+// I_out of its two samples in bytes 0 and 3, Q_out in bytes 1 and 2, all as unsigned bytes with offset 128.  The moments
+// are then plain dp4a sums with non-negative weights; no value-dependent path is left (round 1 detected zero bytes and
+// corrected them in a divergent slow path, which uniform random test data took for two thirds of all vectors).
 #define PACK4(a, b, c, d) ((int)(((unsigned)(a)&255u) | (((unsigned)(b)&255u) << 8) | (((unsigned)(c)&255u) << 16) | (((unsigned)(d)&255u) << 24)))
 
 struct Moments {
     int s0i, s0q, s1i, s1q;
 };
 
+__device__ __forceinline__ unsigned neg_byte3(unsigned u) { return (u ^ 0xff000000u) + 0x01000000u; }
+__device__ __forceinline__ unsigned neg_bytes012(unsigned u) {
+    const unsigned lo = (u ^ 0x00ffffffu) & 0x7f7f7f7fu, hi = (u ^ 0x00ffffffu) & 0x80808080u;
+    return (lo + 0x00010101u) ^ hi;
+}
+
 // accumulate one 16-byte vector whose first sample has in-block index t0 (may be negative at the leading edge;
-// bytes outside the block are already forced to 128)
+// bytes outside the block are already forced to 128, which stays 128 under the byte negation)
 __device__ __forceinline__ void accumulate_vector(Moments &m, const uint4 v, int t0) {
-    // zeroth moment: sum of mixer outputs of the 8 samples
-    int ai = dp4a_us(v.x, PACK4(1, 0, 0, -1), 0);
-    ai = dp4a_us(v.y, PACK4(-1, 0, 0, 1), ai);
-    ai = dp4a_us(v.z, PACK4(1, 0, 0, -1), ai);
-    ai = dp4a_us(v.w, PACK4(-1, 0, 0, 1), ai);
-    int aq = dp4a_us(v.x, PACK4(0, 1, 1, 0), 0);
-    aq = dp4a_us(v.y, PACK4(0, -1, -1, 0), aq);
-    aq = dp4a_us(v.z, PACK4(0, 1, 1, 0), aq);
-    aq = dp4a_us(v.w, PACK4(0, -1, -1, 0), aq);
-    // first moment about the vector's first sample: offsets 0..7
-    int bi = dp4a_us(v.x, PACK4(0, 0, 0, -1), 0);
-    bi = dp4a_us(v.y, PACK4(-2, 0, 0, 3), bi);
-    bi = dp4a_us(v.z, PACK4(4, 0, 0, -5), bi);
-    bi = dp4a_us(v.w, PACK4(-6, 0, 0, 7), bi);
-    int bq = dp4a_us(v.x, PACK4(0, 0, 1, 0), 0);
-    bq = dp4a_us(v.y, PACK4(0, -2, -3, 0), bq);
-    bq = dp4a_us(v.z, PACK4(0, 4, 5, 0), bq);
-    bq = dp4a_us(v.w, PACK4(0, -6, -7, 0), bq);
-    // remove the +128 offset of the bytes: 128 * (sum of weights).  Zeroth-moment weights cancel (1-1-1+1 = 0 for I,
-    // 1+1-1-1-... = 0 for Q); first-moment weights sum to -1-2+3+4-5-6+7 = 0 for I and 0+1-2-3+4+5-6-7 = -8 for Q.
-    bq += 128 * 8;
+    const unsigned x = neg_byte3(v.x), y = neg_bytes012(v.y), z = neg_byte3(v.z), w = neg_bytes012(v.w);
+    // zeroth moment: the 8 mixer outputs of each channel; -128 per byte = -1024
+    int ai = dp4a_us(x, PACK4(1, 0, 0, 1), -1024);
+    ai = dp4a_us(y, PACK4(1, 0, 0, 1), ai);
+    ai = dp4a_us(z, PACK4(1, 0, 0, 1), ai);
+    ai = dp4a_us(w, PACK4(1, 0, 0, 1), ai);
+    int aq = dp4a_us(x, PACK4(0, 1, 1, 0), -1024);
+    aq = dp4a_us(y, PACK4(0, 1, 1, 0), aq);
+    aq = dp4a_us(z, PACK4(0, 1, 1, 0), aq);
+    aq = dp4a_us(w, PACK4(0, 1, 1, 0), aq);
+    // first moment about the vector's first sample (offsets 0..7; -128 * 28 = -3584), accumulated straight into S1
+    int bi = dp4a_us(x, PACK4(0, 0, 0, 1), m.s1i - 3584);
+    bi = dp4a_us(y, PACK4(2, 0, 0, 3), bi);
+    bi = dp4a_us(z, PACK4(4, 0, 0, 5), bi);
+    bi = dp4a_us(w, PACK4(6, 0, 0, 7), bi);
+    int bq = dp4a_us(x, PACK4(0, 0, 1, 0), m.s1q - 3584);
+    bq = dp4a_us(y, PACK4(0, 2, 3, 0), bq);
+    bq = dp4a_us(z, PACK4(0, 4, 5, 0), bq);
+    bq = dp4a_us(w, PACK4(0, 6, 7, 0), bq);
     m.s0i += ai;
     m.s0q += aq;
-    m.s1i += t0 * ai + bi;
-    m.s1q += t0 * aq + bq;
-    // int8 negation wrap for u == 0 (s == -128) at the negated positions: word x byte 3 (I of phase 1),
-    // word y bytes 0,1 (I,Q of phase 2) and byte 2 (Q of phase 3); same for z/w.
-    const unsigned z = ((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) | ((v.z - 0x01010101u) & ~v.z) |
-                       ((v.w - 0x01010101u) & ~v.w);
-    if (z & 0x80808080u) {
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int tk = t0 + 2 * k;        // in-block index of the word's first sample
-            if (k & 1) {
-                if ((w[k] & 0x000000ffu) == 0) { m.s0i -= 256; m.s1i -= 256 * tk; }            // -I, phase 2
-                if ((w[k] & 0x0000ff00u) == 0) { m.s0q -= 256; m.s1q -= 256 * tk; }            // -Q, phase 2
-                if ((w[k] & 0x00ff0000u) == 0) { m.s0q -= 256; m.s1q -= 256 * (tk + 1); }      // Q = -I, phase 3
-            } else {
-                if ((w[k] & 0xff000000u) == 0) { m.s0i -= 256; m.s1i -= 256 * (tk + 1); }      // I = -Q, phase 1
-            }
-        }
-    }
+    m.s1i = t0 * ai + bi;
+    m.s1q = t0 * aq + bq;
 }
 
 // force the bytes of a vector that lie outside [lo, hi) (byte offsets relative to the vector start) to 128

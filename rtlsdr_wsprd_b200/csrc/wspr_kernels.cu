@@ -1210,8 +1210,11 @@ struct FanoQueueFeed {
 // whose lanes are all idle with the queue empty gives its place up FIRST and looks at the queue once more afterwards (a
 // producer may have added work, and the warps launched for that work may have found the pool complete and left), taking
 // the place back if there is something to do -- so work is never stranded, and nobody ever waits for work.
-__global__ void __launch_bounds__(32) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles) {
-    extern __shared__ __align__(16) unsigned char fano_smem[];
+// A CTA carries blockDim.x / 32 worker warps, completely independent of each other (no CTA barrier): with more than one the
+// warps of a CTA sit on different schedulers of their SM, which single-warp CTAs leave to chance.
+__global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles) {
+    extern __shared__ __align__(16) unsigned char fano_smem_all[];
+    unsigned char *fano_smem = fano_smem_all + (size_t)(threadIdx.x >> 5) * FANO_WARP_SMEM_BYTES;
     const unsigned lane = threadIdx.x & 31u;
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1271,8 +1274,9 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *a
 }
 
 int fano_warp_smem_bytes() { return FANO_WARP_SMEM_BYTES; }
-void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st) {
+void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, const DecodeParams &p, cudaStream_t st) {
     if (nwarps <= 0) return;
+    cta_warps = cta_warps == 2 ? 2 : (cta_warps == 4 ? 4 : 1);
     unsigned maxcycles = p.maxcycles;
 #ifdef WSPR_EXPERIMENTS
     // experiment builds only (make exp -> libwsprd_b200_exp.so): cut the long Fano runs short -- WRONG results -- to measure
@@ -1280,7 +1284,8 @@ void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cu
     static const unsigned dbg = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
     if (dbg) maxcycles = dbg;
 #endif
-    k_fano_workers<<<nwarps, 32, FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta, maxcycles);
+    k_fano_workers<<<(nwarps + cta_warps - 1) / cta_warps, 32 * cta_warps, (size_t)cta_warps * FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta,
+                                                                                                                        maxcycles);
     LAUNCHED();
 }
 
@@ -1737,6 +1742,7 @@ void launch_subtract_symbolwise(float *I, float *Q, int np, float f0, int shift,
 // to wait for an SM to drain.
 void init_kernel_attributes(int carveout_kb) {
     cudaFuncSetAttribute(k_sync_freqs_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES);
+    cudaFuncSetAttribute(k_fano_workers, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * FANO_WARP_SMEM_BYTES);
     if (carveout_kb <= 0) return;
     const int pct = std::min(100, (carveout_kb * 100 + 227) / 228);
 #define WSPR_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct)

@@ -199,7 +199,7 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
                      ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
                      cudaStream_t st);
-void launch_fano_workers(FanoQueue *queue, int nwarps, const DecodeParams &p, cudaStream_t st);
+void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, const DecodeParams &p, cudaStream_t st);
 void init_kernel_attributes(int carveout_kb);   // per device: opt-in to > 48 KB of dynamic shared memory, common carve-out
 int fano_warp_smem_bytes();                  // shared memory one worker warp holds
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,

@@ -97,6 +97,8 @@ def library():
     lib.wspr_ctx_upload.argtypes = [vp, vp, vp, C.c_int]
     lib.wspr_ctx_upload_device.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.wspr_ctx_normalise.argtypes = [vp]
+    if hasattr(lib, "wspr_ctx_decimate"):
+        lib.wspr_ctx_decimate.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_size_t]
     lib.wspr_ctx_decode.argtypes = [vp, DecoderOptions]
     lib.wspr_ctx_download.argtypes = [vp, vp, vp, vp, vp]
     lib.wspr_ctx_last_decode_ms.restype = C.c_float
@@ -226,6 +228,13 @@ class BatchDecoder:
         self.ncap = int(ncap)
         _check(self.lib.wspr_ctx_upload_device(self.ctx, int(i_ptr), int(q_ptr), self.ncap,
                                                int(row_stride or self.samples)), "wspr_ctx_upload_device")
+
+    def decimate(self, raw_ptr, nstreams, n_iq, stream_stride_bytes):
+        """Raw u8 IQ streams on the device (16-byte aligned, stream_stride_bytes apart) through the front end straight into
+        this context (rtlsdr_wsprd.c:126-244,285-288); asynchronous.  Follow with normalise() and decode()."""
+        self.ncap = int(nstreams)
+        return _check(self.lib.wspr_ctx_decimate(self.ctx, int(raw_ptr), int(nstreams), int(n_iq), int(stream_stride_bytes)),
+                      "wspr_ctx_decimate")
 
     def normalise(self):
         _check(self.lib.wspr_ctx_normalise(self.ctx), "wspr_ctx_normalise")
