@@ -529,8 +529,8 @@ def run_streams(args):
             d.download(out=spots[lo:lo + n], n_out=hn.numpy()[lo:lo + n])
         return fn
 
-    def step_resident(capture=False):
-        futs = [pipe.submit(job_resident(lo, capture)) for lo in range(0, nstreams, chunk)]
+    def step_resident(capture=False, steps=1):
+        futs = [pipe.submit(job_resident(lo, capture)) for _ in range(steps) for lo in range(0, nstreams, chunk)]
         for f in futs:
             f.result()
 
@@ -539,16 +539,14 @@ def run_streams(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_resident()
+    step_resident(steps=args.warmup)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = w.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        step_resident()
+    step_resident(steps=args.steps)
     torch.cuda.synchronize()
     ev1.record()
     barrier()
@@ -663,6 +661,9 @@ def run_streams(args):
                              "share_of_step": round(k0_total_ms / (total_ms / args.steps), 4)},
                 "cpu_baseline": None, "parity": parity, "corpus_gen_s": round(gen_s, 1)}
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    stages.clear()                                     # (device tensors last used on the contexts' streams: free them while those exist)
+    torch.cuda.empty_cache()
     pipe.close()
     pipe2.close()
     if world > 1:
@@ -716,13 +717,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=-1,
                     help="captures checked against the CPU reference: -1 = all at N=1 / 256 per rank at N>1, 0 = none")
     ap.add_argument("--no-frontend", action="store_true")
-    ap.add_argument("--depth", type=int, default=0, help="batches in flight per GPU (contexts driven by host threads); default 9 (config4: 4)")
+    ap.add_argument("--depth", type=int, default=0, help="batches in flight per GPU (contexts driven by host threads); default 9 (config4: 12)")
     ap.add_argument("--n-iq", type=int, default=N_IQ, help="config4: raw samples per stream")
-    ap.add_argument("--stream-chunk", type=int, default=32, help="config4: streams per decimator launch")
+    ap.add_argument("--stream-chunk", type=int, default=16, help="config4: streams per decimator launch")
     ap.add_argument("--host-streams", type=int, default=8, help="config4: streams of the end-to-end leg (pinned host memory)")
     args = ap.parse_args()
     args.units = args.units or DEFAULT_UNITS[args.workload]
-    args.depth = args.depth or (4 if args.workload == "config4" else 9)
+    args.depth = args.depth or (12 if args.workload == "config4" else 9)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

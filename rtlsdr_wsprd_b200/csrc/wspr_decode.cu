@@ -77,6 +77,8 @@ static void host_tables(HostTables &t) {
 // not linked, the entry points come from cudaGetDriverEntryPoint): the workers then never share an SM -- its issue slots, its
 // shared-memory carve-out -- with the bulk kernels, which get the remaining SMs.
 //   WSPR_FANO_SMS   SMs set aside for the pool (even; 0 = no partition, workers and bulk kernels share every SM)
+//   WSPR_FANO_SHARE 1: the pool is confined to its WSPR_FANO_SMS SMs but the other kernels run on ALL SMs (they use whatever
+//                   the workers leave of those SMs); 0: the other kernels keep off the pool's SMs
 //   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
 //                   per SM unpartitioned)
 //   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
@@ -88,6 +90,9 @@ static void host_tables(HostTables &t) {
 #endif
 #ifndef WSPR_DEFAULT_CARVEOUT_KB
 #define WSPR_DEFAULT_CARVEOUT_KB 164              // K4's two 47 KB CTAs + two worker warps; measured in profiles/r2_bench_variants.txt
+#endif
+#ifndef WSPR_DEFAULT_FANO_SHARE
+#define WSPR_DEFAULT_FANO_SHARE 0
 #endif
 #ifndef WSPR_DEFAULT_FANO_CTA_WARPS
 #define WSPR_DEFAULT_FANO_CTA_WARPS 1
@@ -105,6 +110,7 @@ struct FanoService {
     int device = -1;
     int fano_sms = 0, pool = 0, total_sms = 0, cta_warps = 1;
     bool partitioned = false;
+    bool shared_bulk = false;                      // the other kernels may use the pool's SMs as well (WSPR_FANO_SHARE)
     CUgreenCtx g_fano = nullptr, g_bulk = nullptr;
     FanoQueue *queue = nullptr;                    // device
     FanoQueueEntry *ring = nullptr;                // device
@@ -168,6 +174,7 @@ static FanoService *fano_service(int device) {
         if (!s->partitioned) s->note = "SM partition unavailable (green contexts): Fano workers share the SMs";
     }
     if (!s->partitioned) s->fano_sms = 0;
+    s->shared_bulk = s->partitioned && env_int("WSPR_FANO_SHARE", WSPR_DEFAULT_FANO_SHARE) != 0;
     const int per_sm = (228 * 1024) / (fano_warp_smem_bytes() + 1024);
     s->pool = env_int("WSPR_FANO_POOL", s->partitioned ? s->fano_sms * per_sm : s->total_sms * WSPR_DEFAULT_FANO_POOL_PER_SM);
     if (s->pool < 1) s->pool = 1;
@@ -187,7 +194,7 @@ static FanoService *fano_service(int device) {
 }
 
 static cudaError_t service_stream(FanoService *s, bool fano, cudaStream_t *out) {
-    if (s->partitioned) {
+    if (s->partitioned && (fano || !s->shared_bulk)) {
         static auto pStream = driver_entry<CUresult (*)(CUstream *, CUgreenCtx, unsigned, int)>("cuGreenCtxStreamCreate");
         CUstream st = nullptr;
         if (!pStream || pStream(&st, fano ? s->g_fano : s->g_bulk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return cudaErrorUnknown;
