@@ -189,6 +189,9 @@ static FanoService *fano_service(int device) {
         cudaMalloc((void **)&s->queue, sizeof(FanoQueue)) != cudaSuccess) { delete s; return nullptr; }
     h.ring = s->ring;
     if (cudaMemcpy(s->queue, &h, sizeof h, cudaMemcpyHostToDevice) != cudaSuccess) { delete s; return nullptr; }
+#ifdef WSPR_EXPERIMENTS
+    exp_set_queue(s->queue);
+#endif
     g_svc[device] = s;
     return s;
 }
@@ -733,6 +736,14 @@ extern "C" int wspr_fano_stats(int device, unsigned long long *out8, int reset) 
     if (reset) CK(cudaMemset(&s->queue->st_warp_periods, 0, 5 * sizeof(unsigned long long)));
     return WSPR_OK;
 }
+
+#ifdef WSPR_EXPERIMENTS
+// experiment builds only: out16 = [kernel 0: K4, 1: LPF][worker warps on the SM: 0,1,2,3+][sum of clocks, warps]
+extern "C" int wspr_debug_hist(unsigned long long *out16, int reset) {
+    exp_read_hist(out16, reset);
+    return WSPR_OK;
+}
+#endif
 
 extern "C" int wspr_ctx_time_kernels(wspr_ctx *c, int on) {
     if (!c) return WSPR_ERR_ARG;

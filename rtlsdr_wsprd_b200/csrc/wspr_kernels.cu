@@ -22,6 +22,42 @@ extern unsigned long long g_frontend_launches;   // wspr_frontend.cu
 unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend_launches; }
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
+#ifdef WSPR_EXPERIMENTS
+// experiment builds only: how long do the warps of the bulk kernels run on SMs that host 0, 1, 2, 3+ Fano worker warps?
+// g_exp_hist[kernel][workers on the SM when the warp started][0: sum of clocks, 1: warps]
+__device__ FanoQueue *g_exp_queue;
+__device__ unsigned long long g_exp_hist[2][4][2];
+struct ExpTimer {
+    long long t0;
+    int nw, kernel;
+    __device__ ExpTimer(int k) : kernel(k) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        nw = g_exp_queue ? min(3, max(0, *(volatile int *)&g_exp_queue->sm_workers[smid & 255u])) : 0;
+        t0 = clock64();
+    }
+    __device__ void stop() {
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&g_exp_hist[kernel][nw][0], (unsigned long long)(clock64() - t0));
+            atomicAdd(&g_exp_hist[kernel][nw][1], 1ull);
+        }
+    }
+};
+void exp_set_queue(FanoQueue *q) { cudaMemcpyToSymbol(g_exp_queue, &q, sizeof q); }
+void exp_read_hist(unsigned long long *out16, int reset) {
+    cudaMemcpyFromSymbol(out16, g_exp_hist, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_exp_hist, z, sizeof z);
+    }
+}
+#define EXP_TIMER(k) ExpTimer exp_timer(k)
+#define EXP_STOP() exp_timer.stop()
+#else
+#define EXP_TIMER(k)
+#define EXP_STOP()
+#endif
+
 // ---- constant tables ----------------------------------------------------------------------------------
 __device__ float c_window_g[NFFT];    // (indexed in bit-reversed order by the lanes: global/L1, not the constant bank)
 __constant__ float c_lpf_w[NFILT];
@@ -281,7 +317,8 @@ constexpr int COARSE_RANKS = 16;            // grid width; a CTA strides over th
 __global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, Cand *__restrict__ cands,
                                                 const CapState *__restrict__ caps, const int *__restrict__ list, int blocks) {
     extern __shared__ float sq[];           // [blocks][COARSE_BINS] sqrt(ps)
-    __shared__ float s_sync[288];
+    __shared__ float s_sync[288 / 32];
+    __shared__ int s_arg[288 / 32];
     const int cap = list[blockIdx.y], t = threadIdx.x;
     const int npk = caps[cap].npk, maxdrift = pass_maxdrift(caps[cap].ipass);
   for (int rank = blockIdx.x; rank < npk; rank += COARSE_RANKS) {
@@ -305,7 +342,9 @@ __global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, C
     if (valid) {
         float ss = 0.0f, pw = 0.0f;
         for (int k = 0; k < NSYM; k++) {
-            int ifd = (int)(ifr + (double)((((float)k - (float)NBITS) / (float)NBITS) * (float)idrift) / 375.0 / 256.0);
+            // ifd = (int)(ifr + ((k - 81) / 81 * idrift) / 375.0 / 256.0), :655: the drift term is a few 1e-5 of a bin, so the
+            // truncation gives ifr - 1 when the term is negative and ifr otherwise (ifr >= 100: the sum stays positive)
+            const int ifd = ifr - (((idrift < 0 && k > NBITS) || (idrift > 0 && k < NBITS)) ? 1 : 0);
             int kx = k0 + 2 * k;
             if (kx < blocks) {
                 int row = kx, col = ifd - lo;
@@ -322,17 +361,33 @@ __global__ void __launch_bounds__(288) k_coarse(const float *__restrict__ psT, C
         }
         sync = ss / pw;
     }
-    s_sync[t] = sync;
+    // arg-max in loop order (:668, strict '>': the first of equal maxima wins, NaN never wins): warp-level (value, index)
+    // reduction, then the nine warp winners
+    float bv = (sync > -1e30f) ? sync : -CUDART_INF_F;      // (NaN and values that can never win)
+    int bi = t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    if ((t & 31) == 0) {
+        s_sync[t >> 5] = bv;
+        s_arg[t >> 5] = bi;
+    }
     __syncthreads();
     if (t == 0) {
-        float best = -1e30f;
+        float best = -CUDART_INF_F;
         int arg = -1;
-        for (int h = 0; h < 288; h++)
-            if (s_sync[h] > best) {
-                best = s_sync[h];
-                arg = h;
+        for (int wq = 0; wq < 288 / 32; wq++)               // (warps hold ascending index ranges)
+            if (s_sync[wq] > best) {
+                best = s_sync[wq];
+                arg = s_arg[wq];
             }
-        if (arg >= 0) {
+        if (arg >= 0 && best > -1e30f) {
             int bk0 = -10 + (arg / 3) % 32, bd = arg % 3;
             c->shift = 128 * (bk0 + 1);
             c->drift = (float)((bd == 0) ? -maxdrift : (bd == 1 ? 0 : 1));
@@ -557,6 +612,7 @@ __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const f
     }
     if (shared_tab) load_tables(tab, tabs, blockIdx.x, 2, t, LAG_THREADS);
     __syncthreads();
+    EXP_TIMER(0);
 
     const int sym_local = t / nlags, lagidx = t - sym_local * nlags;
     const int sym = g * SYMS_PER_CTA + sym_local;
@@ -607,6 +663,7 @@ __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const f
         power = acc_power(a);
     }
     P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = power;
+    EXP_STOP();
 }
 
 // per-lag sync metric and arg-max over lags (:216-218,227-232); one warp-sized CTA per job
@@ -1530,6 +1587,7 @@ __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, 
         sc[(m % LPF_R) * LPF_PITCH + m / LPF_R] = (g < CPAD) ? src[m] : make_float2(0.0f, 0.0f);
     }
     __syncthreads();
+    EXP_TIMER(1);
     pk2 acc[LPF_R];                                          // (i, q) sums side by side (packed pairs, see pk_mul/pk_add)
     pk2 w[LPF_R];                                            // sliding window: inputs 4t+tap .. 4t+tap+3
     const pk2 *scp = reinterpret_cast<const pk2 *>(sc);
@@ -1558,6 +1616,7 @@ __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, 
         ai[r] = pk_lo(acc[r]);
         aq[r] = pk_hi(acc[r]);
     }
+    EXP_STOP();
 #pragma unroll
     for (int r = 0; r < LPF_R; r++) {                         // :397-410
         int i = i0 + LPF_R * t + r;

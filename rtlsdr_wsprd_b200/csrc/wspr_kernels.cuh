@@ -225,5 +225,9 @@ void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t strea
 int decimate_outputs(size_t n_iq);
 
 unsigned long long kernel_launch_count();
+#ifdef WSPR_EXPERIMENTS
+void exp_set_queue(FanoQueue *q);
+void exp_read_hist(unsigned long long *out16, int reset);
+#endif
 
 }  // namespace wspr

@@ -76,12 +76,20 @@ WMATH double reduce_small(double x, int *np) {
     return fma(-(double)n, HPI, x);
 }
 
-// larger arguments: 96 bits of 4/pi selected by the exponent
+// larger arguments: 96 bits of 4/pi selected by the exponent.  (On the device the table sits in global memory: as a local
+// array every thread rebuilt it on its stack -- 24 stores and three local loads per call, which is what bound k_sub_ref.)
+#define WSPR_INV_PIO4 {0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, \
+                       0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, \
+                       0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041}
+#ifdef __CUDACC__
+static __device__ const uint32_t g_inv_pio4[24] = WSPR_INV_PIO4;
+#endif
 WMATH double reduce_big(uint32_t xi, int *np) {
-    const uint32_t inv_pio4[24] = {0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44,
-                                   0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1,
-                                   0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62,
-                                   0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+#ifdef __CUDA_ARCH__
+    const uint32_t *inv_pio4 = g_inv_pio4;
+#else
+    static const uint32_t inv_pio4[24] = WSPR_INV_PIO4;
+#endif
     const double PI63 = 0x1.921FB54442D18p-62;
     const uint32_t *arr = &inv_pio4[(xi >> 26) & 15];
     int shift = (xi >> 23) & 7;
