@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -157,6 +158,84 @@ __global__ void __launch_bounds__(MOM_WARPS * 32) k_block_moments(const uint8_t 
     if (lane == 0) moments[(size_t)stream * nblk + b] = make_uint4((unsigned)m.s0i, (unsigned)m.s0q, (unsigned)m.s1i, (unsigned)m.s1q);
 }
 
+// The same pass with the block staged through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, the 1-D form
+// of TMA): one warp per block as above, the block's covering vectors fetched as MOMB_PIECES bulk copies of 16-byte-aligned
+// ranges into the warp's slab, each completing on its own mbarrier, so the first piece is summed while the others are in
+// flight.  Selected with WSPR_K0_BULK=1 (an A/B of the load path: profiles/r2_k0_bulk_ab.txt); the arithmetic is identical.
+constexpr int MOMB_WARPS = 4;
+constexpr int MOMB_PIECES = 4;
+constexpr int MOMB_SLAB = 803 * 16;                           // a block spans at most 802 vectors
+constexpr int MOMB_SMEM = MOMB_WARPS * MOMB_SLAB;
+__device__ __forceinline__ uint4 lds_vec(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__global__ void __launch_bounds__(MOMB_WARPS * 32) k_block_moments_bulk(const uint8_t *__restrict__ raw, size_t stream_stride,
+                                                                       int nblk, uint4 *__restrict__ moments, int first_byte) {
+    extern __shared__ __align__(128) unsigned char momb_smem[];
+    __shared__ __align__(8) unsigned long long mbar[MOMB_WARPS][MOMB_PIECES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * MOMB_WARPS + warp, stream = blockIdx.y;
+    if (b >= nblk) return;                                     // (warps are independent: no CTA barrier below)
+    const uint8_t *base = raw + (size_t)stream * stream_stride;
+    const long long byte0 = (long long)first_byte + (long long)b * BLOCK_BYTES, byte1 = byte0 + BLOCK_BYTES;
+    const long long v0 = byte0 >> 4, v1 = (byte1 + 15) >> 4;
+    const int nvec = (int)(v1 - v0);
+    const uint4 *vp = reinterpret_cast<const uint4 *>(base) + v0;
+    const int lead = (int)(byte0 - (v0 << 4)), tail = (int)((v1 << 4) - byte1);
+    const int tfirst = -(lead >> 1);
+    const unsigned slab = (unsigned)__cvta_generic_to_shared(momb_smem + (size_t)warp * MOMB_SLAB);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&mbar[warp][0]);
+    const int per = (nvec + MOMB_PIECES - 1) / MOMB_PIECES;
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < MOMB_PIECES; p++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * p), "r"(1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int p = 0; p < MOMB_PIECES; p++) {
+            const int p0 = p * per, p1 = min(p0 + per, nvec);
+            const unsigned bytes = (unsigned)(p1 - p0) * 16u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * p), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slab + 16u * p0),
+                         "l"(vp + p0), "r"(bytes), "r"(bar0 + 8u * p)
+                         : "memory");
+        }
+    }
+    __syncwarp();
+    Moments m = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int p = 0; p < MOMB_PIECES; p++) {
+        unsigned ok;
+        do {
+            asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(ok)
+                         : "r"(bar0 + 8u * p), "r"(0)
+                         : "memory");
+        } while (!ok);
+        const int p0 = max(p * per, 1), p1 = min(min(p * per + per, nvec), nvec - 1);   // interior vectors of the piece
+        int i = p0 + lane;
+        for (; i + 32 * (MOM_UNROLL - 1) < p1; i += 32 * MOM_UNROLL) {
+            uint4 v[MOM_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MOM_UNROLL; u++) v[u] = lds_vec(slab + 16u * (i + 32 * u));
+#pragma unroll
+            for (int u = 0; u < MOM_UNROLL; u++) accumulate_vector(m, v[u], tfirst + 8 * (i + 32 * u));
+        }
+        for (; i < p1; i += 32) accumulate_vector(m, lds_vec(slab + 16u * i), tfirst + 8 * i);
+    }
+    if (lane == 0) accumulate_vector(m, mask_vector(lds_vec(slab), lead, 16), tfirst);
+    if (lane == 1) accumulate_vector(m, mask_vector(lds_vec(slab + 16u * (nvec - 1)), 0, 16 - tail), tfirst + 8 * (nvec - 1));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        m.s0i += __shfl_xor_sync(0xffffffffu, m.s0i, s);
+        m.s0q += __shfl_xor_sync(0xffffffffu, m.s0q, s);
+        m.s1i += __shfl_xor_sync(0xffffffffu, m.s1i, s);
+        m.s1q += __shfl_xor_sync(0xffffffffu, m.s1q, s);
+    }
+    if (lane == 0) moments[(size_t)stream * nblk + b] = make_uint4((unsigned)m.s0i, (unsigned)m.s0q, (unsigned)m.s1i, (unsigned)m.s1q);
+}
+
 // Second pass: v = (b+1)*6401*P - W with the wrapping prefix sums P = sum S0, W = sum (b*6401*S0 + S1), the two combs and
 // the FIR.  One CTA per CF_CHUNK outputs of a stream: it first sums the moments of every earlier block of its stream (a
 // redundant prefix, 16 bytes per block out of L2 -- 3 % of the traffic of the first pass), then scans its own blocks
@@ -279,8 +358,21 @@ void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t strea
     if (nstreams <= 0 || max_out <= 0) return;
     upload_fir();
     if (nblk > 0) {
-        k_block_moments<<<dim3((nblk + MOM_WARPS - 1) / MOM_WARPS, nstreams), MOM_WARPS * 32, 0, st>>>(raw, stream_stride_bytes,
-                                                                                                      nblk, (uint4 *)moments, 0);
+        static const bool bulk = [] { const char *e = getenv("WSPR_K0_BULK"); return e && e[0] == '1'; }();   // load-path A/B
+        if (bulk) {
+            static bool attr[64] = {false};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 64 && !attr[dev]) {
+                cudaFuncSetAttribute(k_block_moments_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, MOMB_SMEM);
+                attr[dev] = true;
+            }
+            k_block_moments_bulk<<<dim3((nblk + MOMB_WARPS - 1) / MOMB_WARPS, nstreams), MOMB_WARPS * 32, MOMB_SMEM, st>>>(
+                raw, stream_stride_bytes, nblk, (uint4 *)moments, 0);
+        } else {
+            k_block_moments<<<dim3((nblk + MOM_WARPS - 1) / MOM_WARPS, nstreams), MOM_WARPS * 32, 0, st>>>(raw, stream_stride_bytes,
+                                                                                                          nblk, (uint4 *)moments, 0);
+        }
         g_frontend_launches++;
     }
     k_comb_fir<<<dim3((max_out + CF_CHUNK - 1) / CF_CHUNK, nstreams), CF_THREADS, 0, st>>>(moments, nblk, I, Q, out_stride, max_out);

@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu.log
+WSPR_K0_BULK=1 timeout 600 python -m pytest tests -m gpu -x -q -k "frontend or streaming" > gpurun_out/r2_pytest_k0bulk.log 2>&1; tail -2 gpurun_out/r2_pytest_k0bulk.log
+{ echo "# tools/profile_frontend.py 8 (8 full-length streams of uniform random bytes resident in HBM; k_block_moments + k_comb_fir, CUDA events)"; echo "# --- plain 16-byte loads (ld.global.nc.L1::no_allocate)"; timeout 120 python tools/profile_frontend.py 8; echo "# --- WSPR_K0_BULK=1: cp.async.bulk + mbarrier staging through shared memory"; WSPR_K0_BULK=1 timeout 120 python tools/profile_frontend.py 8; echo "# --- plain again"; timeout 120 python tools/profile_frontend.py 8; } > gpurun_out/r2_k0_bulk_ab.txt 2>&1; cat gpurun_out/r2_k0_bulk_ab.txt
 WSPR_B200_LIB=$PWD/rtlsdr_wsprd_b200/libwsprd_b200_exp.so timeout 300 python tools/exp_warp_times.py > gpurun_out/r2_warp_times.txt 2>&1; cat gpurun_out/r2_warp_times.txt
 WSPR_B200_LIB=$PWD/rtlsdr_wsprd_b200/libwsprd_b200_exp.so WSPR_FANO_PER_SM=0 timeout 300 python tools/exp_warp_times.py > gpurun_out/r2_warp_times_nocap.txt 2>&1; cat gpurun_out/r2_warp_times_nocap.txt
 B="python bench.py --steps 8 --warmup 4 --cpu-sample 0 --no-frontend"
