@@ -121,7 +121,8 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
     const unsigned limit = maxcycles * (unsigned)nbits;
     const float inv_delta = 1.0f / (float)delta;
 
-    bool act = false, busy = false, inback = false;
+    bool act = false, busy = false;
+    unsigned inback = 0;                           // 1: this trip continues a walk back (no new Fano cycle)
     int pos = 0, thr = PARKED, gam = 0, pgam = 0, maxnp = 0;
     unsigned it = 0, stop = 0xffffffffu;           // Fano cycles started so far; cycle budget of this attempt
     unsigned w = 0, enc = 0, cur = 0;              // cur: biased metric of the branch being tried
@@ -137,7 +138,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
                 r_cycles = limit + 2u;
                 r_maxnp = 0u;
             }
-            if (act && !inback && (it >= stop || feed.abandon())) {
+            if (act && inback == 0 && (it >= stop || feed.abandon())) {
                 act = false;
                 r_rc = FANO_STOPPED;
                 r_metric = (unsigned)gam;
@@ -204,7 +205,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
                     }
                     const unsigned w0 = mem.ldl(0).x;  // root: encoder state 0, branch symbol 0 -> pair {0,3}, lower symbol
                     act = busy = true;
-                    inback = false;
+                    inback = 0;
                     pos = 0;
                     thr = 0;
                     gam = pgam = 0;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
                     cur = w & 0x1ffu;
                 } else {                           // park
                     thr = PARKED;
-                    inback = false;
+                    inback = 0;
                 }
             }
             feed.period(act);
@@ -226,7 +227,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
         const uint2 nl = mem.ldl(pos + 1);
         const unsigned nd = mem.ldn(pos - 1);
         const int ng = gam + (int)cur - FANO_BIAS;
-        const bool newc = !inback;                 // this trip opens a new Fano cycle
+        const bool newc = inback == 0;             // this trip opens a new Fano cycle
         const bool fwd = newc && (ng >= thr);
         const bool tig = newc && !fwd && (pos == 0 || pgam < thr);
         const bool bck = !fwd && !tig;
@@ -240,7 +241,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
             r_cycles = limit + 2u;
             r_maxnp = (unsigned)maxnp;
         }
-        it += newc ? 1u : 0u;
+        it += 1u - inback;
         if (EXACT) maxnp = newc ? max(maxnp, pos) : maxnp;
         // ---- forward: raise the threshold on a first visit, remember the node, descend along the better branch
         int thrF = thr;
@@ -280,7 +281,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
         enc = fwd ? encF : (bck ? encB : (enc ^ (w >> 31)));
         w = fwd ? wF : (bck ? wB : (w & 0x7fffffffu));
         cur = (((int)w < 0) ? (w >> 9) : w) & 0x1ffu;
-        inback = bck && !b1 && !b2;
+        inback = (bck && !b1 && !b2) ? 1u : 0u;
         pos = posN;
         if (arrived) {                             // reached the last node: decoded (rare, once per attempt)
             if (act) {
@@ -292,7 +293,7 @@ __device__ __forceinline__ void fano_run_impl(Feed &feed, Mem mem, const short *
                 r_enc = encT;                      // encoder state of the last node
             }
             thr = PARKED;                          // park: stay put (pos = nbits - 1), tightening an unreachable threshold
-            inback = false;
+            inback = 0;
         }
     }
 }

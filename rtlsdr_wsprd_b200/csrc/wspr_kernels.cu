@@ -23,26 +23,39 @@ unsigned long long kernel_launch_count() { return g_launches.load() + g_frontend
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
 #ifdef WSPR_EXPERIMENTS
-// experiment builds only: how long do the warps of the bulk kernels run on SMs that host 0, 1, 2, 3+ Fano worker warps?
-// g_exp_hist[kernel][workers on the SM when the warp started][0: sum of clocks, 1: warps]
+// experiment builds only: how long do the warps of the bulk kernels run on SMs that host Fano worker warps, and does it
+// matter whether a worker sits on the warp's own scheduler (SMSP = warp id % 4)?
+// g_exp_hist[kernel][class][0: sum of clocks, 1: warps]; class 0: no worker on the SM, 1: worker(s) on the SM but not on this
+// warp's scheduler, 2: one worker on this warp's scheduler, 3: two or more
 __device__ FanoQueue *g_exp_queue;
 __device__ unsigned long long g_exp_hist[2][4][2];
+__device__ int g_exp_smsp[256][4];                 // worker warps per (SM, scheduler)
 struct ExpTimer {
     long long t0;
-    int nw, kernel;
+    int cls, kernel;
     __device__ ExpTimer(int k) : kernel(k) {
-        unsigned smid;
+        unsigned smid, wid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        nw = g_exp_queue ? min(3, max(0, *(volatile int *)&g_exp_queue->sm_workers[smid & 255u])) : 0;
+        asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+        smid &= 255u;
+        const volatile int *v = g_exp_smsp[smid];
+        const int mine = v[wid & 3u], all = v[0] + v[1] + v[2] + v[3];
+        cls = mine >= 2 ? 3 : (mine == 1 ? 2 : (all > 0 ? 1 : 0));
         t0 = clock64();
     }
     __device__ void stop() {
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&g_exp_hist[kernel][nw][0], (unsigned long long)(clock64() - t0));
-            atomicAdd(&g_exp_hist[kernel][nw][1], 1ull);
+            atomicAdd(&g_exp_hist[kernel][cls][0], (unsigned long long)(clock64() - t0));
+            atomicAdd(&g_exp_hist[kernel][cls][1], 1ull);
         }
     }
 };
+__device__ void exp_worker_mark(int delta) {
+    unsigned smid, wid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+    atomicAdd(&g_exp_smsp[smid & 255u][wid & 3u], delta);
+}
 void exp_set_queue(FanoQueue *q) { cudaMemcpyToSymbol(g_exp_queue, &q, sizeof q); }
 void exp_read_hist(unsigned long long *out16, int reset) {
     cudaMemcpyFromSymbol(out16, g_exp_hist, sizeof(unsigned long long) * 16);
@@ -53,9 +66,11 @@ void exp_read_hist(unsigned long long *out16, int reset) {
 }
 #define EXP_TIMER(k) ExpTimer exp_timer(k)
 #define EXP_STOP() exp_timer.stop()
+#define EXP_WORKER(d) do { if ((threadIdx.x & 31) == 0) exp_worker_mark(d); } while (0)
 #else
 #define EXP_TIMER(k)
 #define EXP_STOP()
+#define EXP_WORKER(d)
 #endif
 
 // ---- constant tables ----------------------------------------------------------------------------------
@@ -726,14 +741,25 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
     const bool inside = (start > 0) && (start + SPS <= np);
     float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (!shared_tab) tone_seeds(fp, cd, sd);
-    if (shared_tab && inside && ((start & 3) == 0)) {          // the common case, packed like k_sync_lags
-        const float4 *i4 = reinterpret_cast<const float4 *>(ip + start), *q4 = reinterpret_cast<const float4 *>(qp + start);
+    if (shared_tab && inside) {                                // the common case, packed like k_sync_lags
         const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
         pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
+        const bool aligned = (start & 3) == 0;                 // (jittered windows start at shift +- 3k: scalar loads then)
+        const float4 *i4 = reinterpret_cast<const float4 *>(ip + (aligned ? start : 0)), *q4 = reinterpret_cast<const float4 *>(qp + (aligned ? start : 0));
 #pragma unroll 2
         for (int j4 = 0; j4 < SPS / 4; j4++) {
-            float4 xi = i4[j4], xq = q4[j4];
-            float xs[4] = {xi.x, xi.y, xi.z, xi.w}, ys[4] = {xq.x, xq.y, xq.z, xq.w};
+            float xs[4], ys[4];
+            if (aligned) {
+                const float4 xi = i4[j4], xq = q4[j4];
+                xs[0] = xi.x; xs[1] = xi.y; xs[2] = xi.z; xs[3] = xi.w;
+                ys[0] = xq.x; ys[1] = xq.y; ys[2] = xq.z; ys[3] = xq.w;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    xs[r] = ip[start + j4 * 4 + r];
+                    ys[r] = qp[start + j4 * 4 + r];
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const pk2 x = pk_make(xs[r], xs[r]), y = pk_make(ys[r], ys[r]), n = pk_make(-xs[r], -xs[r]);
@@ -1291,6 +1317,7 @@ __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q,
     }
     mine = __shfl_sync(0xffffffffu, mine, 0);
     if (!mine) return;
+    EXP_WORKER(1);
     FanoQueueFeed feed{q, nullptr, 0, 0u, 0u, 0u, 0u};
     while (mine) {
         fano_run<false>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);
@@ -1308,6 +1335,7 @@ __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q,
     }
     const unsigned busy = __reduce_add_sync(0xffffffffu, feed.busy_periods), att = __reduce_add_sync(0xffffffffu, feed.attempts),
                    drop = __reduce_add_sync(0xffffffffu, feed.dropped);
+    EXP_WORKER(-1);
     if (lane == 0) {
         if (*(volatile int *)&q->per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
         atomicAdd(&q->st_warp_periods, (unsigned long long)feed.periods);

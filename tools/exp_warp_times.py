@@ -23,7 +23,7 @@ with w.PipelinedDecoder(depth, n) as pipe:
 h = np.array(list(hist), dtype=np.float64).reshape(2, 4, 2)
 for k, name in enumerate(("k_sync_lags", "k_sub_lpf")):
     base = h[k, 0, 0] / max(h[k, 0, 1], 1)
-    for nw in range(4):
-        cnt = h[k, nw, 1]
-        avg = h[k, nw, 0] / max(cnt, 1)
-        print("%-12s worker warps on the SM %d%s: %10d warps, mean %9.0f clocks (x%.3f)" % (name, nw, "+" if nw == 3 else " ", cnt, avg, avg / base if base else 0))
+    for cls, what in enumerate(("no worker on the SM", "workers on the SM, none on this scheduler", "one worker on this scheduler", "two or more on this scheduler")):
+        cnt = h[k, cls, 1]
+        avg = h[k, cls, 0] / max(cnt, 1)
+        print("%-12s %-42s: %10d warps, mean %9.0f clocks (x%.3f)" % (name, what, cnt, avg, avg / base if base else 0))
