@@ -730,8 +730,10 @@ def main():
     elif args.workload == "config4":
         run_streams(args)
     else:
-        if args.workload == "config5" and args.steps > 3:
-            args.steps, args.warmup = 2, 3            # 12 500 captures per GPU per step: keep the run to a few minutes
+        if args.workload == "config5":
+            args.resident = max(args.resident, args.units)     # every capture of the shard is distinct in both legs
+            if args.steps > 3:
+                args.steps, args.warmup = 2, 3        # 12 500 captures per GPU per step: keep the run to a few minutes
         run_captures(args)
 
 

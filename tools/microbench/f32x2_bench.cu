@@ -65,6 +65,7 @@ int main() {
     const int iters = 100000;
     const u64 NZ = 0x8000000080000000ull, ONE = 0x3f8000003f800000ull;
     const char *names[4] = {"scalar FMUL+FADD", "packed unfused (2 FFMA2 per mul+add pair)", "packed fused FFMA2", "scalar FFMA"};
+    double best_unfused = 0.0;
     for (int mode = 0; mode < 4; mode++) {
         for (int rep = 0; rep < 2; rep++) {
             cudaEventRecord(e0);
@@ -77,9 +78,12 @@ int main() {
             float ms;
             cudaEventElapsedTime(&ms, e0, e1);
             double pairs = 148.0 * 8 * 256 * (double)iters * 16;       // multiply-accumulate lane operations
-            printf("mode %d (%s): %.2f ms, %.2f T mul+acc pairs/s = %.1f per clk per SM at 1.965 GHz\n", mode, names[mode], ms,
-                   pairs / ms / 1e9, pairs / ms / 1e3 / 148 / 1.965e9 * 1e3 / 1e3);
+            printf("mode %d (%s): %.2f ms, %.2f T mul+acc pairs/s\n", mode, names[mode], ms, pairs / ms / 1e9);
+            if (mode == 1 && 2.0 * pairs / ms / 1e9 > best_unfused) best_unfused = 2.0 * pairs / ms / 1e9;
         }
     }
+    // the ceiling the correlation / low-pass kernels are measured against: one rounded multiply and one rounded add per pair
+    printf("{\"unfused_tflops\": %.3f, \"how\": \"tools/microbench/f32x2_bench.cu mode 1: nothing but exact-product / exact-sum FFMA2 pairs, 148 x 8 CTAs of 256 threads, 8 independent chains per thread\"}\n",
+           best_unfused);
     return 0;
 }
