@@ -535,6 +535,41 @@ __device__ __forceinline__ float4 acc_power(const Acc8 &a) {   // :211-214  (dou
     return p;
 }
 
+// Drifting candidates (5 % of all): every symbol has its own frequency, so the four phasors advance in registers by the
+// reference's recurrence (:181-187: c' = c*cd - s*sd, s' = c*sd + s*cd, every product and sum rounded separately).  Packed
+// like the table path: tones (0,1) and (2,3) side by side; a - b is a + (-b) and s*(-sd) is -(s*sd), both exactly.
+struct DriftPhasors {
+    pk2 c01, s01, c23, s23, cd01, sd01, nsd01, cd23, sd23, nsd23;
+};
+__device__ __forceinline__ void drift_init(DriftPhasors &p, float fp) {
+    float cd[4], sd[4];
+    tone_seeds(fp, cd, sd);
+    p.cd01 = pk_make(cd[0], cd[1]);
+    p.cd23 = pk_make(cd[2], cd[3]);
+    p.sd01 = pk_make(sd[0], sd[1]);
+    p.sd23 = pk_make(sd[2], sd[3]);
+    p.nsd01 = pk_make(-sd[0], -sd[1]);
+    p.nsd23 = pk_make(-sd[2], -sd[3]);
+    p.c01 = p.c23 = pk_make(1.0f, 1.0f);
+    p.s01 = p.s23 = pk_make(0.0f, 0.0f);
+}
+__device__ __forceinline__ void drift_step(pk2 &ai01, pk2 &aq01, pk2 &ai23, pk2 &aq23, float xf, float yf, DriftPhasors &p, pk2 negzero,
+                                           pk2 one) {
+    const pk2 x = pk_make(xf, xf), y = pk_make(yf, yf), n = pk_make(-xf, -xf);
+    ai01 = pk_add(pk_add(ai01, pk_mul(x, p.c01, negzero), one), pk_mul(y, p.s01, negzero), one);
+    aq01 = pk_add(pk_add(aq01, pk_mul(n, p.s01, negzero), one), pk_mul(y, p.c01, negzero), one);
+    ai23 = pk_add(pk_add(ai23, pk_mul(x, p.c23, negzero), one), pk_mul(y, p.s23, negzero), one);
+    aq23 = pk_add(pk_add(aq23, pk_mul(n, p.s23, negzero), one), pk_mul(y, p.c23, negzero), one);
+    const pk2 cn01 = pk_add(pk_mul(p.c01, p.cd01, negzero), pk_mul(p.s01, p.nsd01, negzero), one);
+    const pk2 sn01 = pk_add(pk_mul(p.c01, p.sd01, negzero), pk_mul(p.s01, p.cd01, negzero), one);
+    const pk2 cn23 = pk_add(pk_mul(p.c23, p.cd23, negzero), pk_mul(p.s23, p.nsd23, negzero), one);
+    const pk2 sn23 = pk_add(pk_mul(p.c23, p.sd23, negzero), pk_mul(p.s23, p.cd23, negzero), one);
+    p.c01 = cn01;
+    p.s01 = sn01;
+    p.c23 = cn23;
+    p.s23 = sn23;
+}
+
 // ---- mode 0: all lags of a group of SYMS_PER_CTA symbols, IQ window staged in shared memory ----------------
 // The window is stored transposed, sample m at [m % 8][m / 8], so that lanes holding consecutive lags (8 samples
 // apart) read consecutive shared-memory words.  The cells of the group are numbered lag-fastest and dealt to the
@@ -656,25 +691,19 @@ __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const f
         a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
         power = acc_power(a);
     } else {
-        Acc8 a;
-#pragma unroll
-        for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
-        float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        tone_seeds(symbol_freq(f0, drift, sym), cd, sd);
+        DriftPhasors ph;
+        drift_init(ph, symbol_freq(f0, drift, sym));
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
         for (int j8 = 0; j8 < SPS / 8; j8++) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 v = wp[r * LAG_PITCH + j8];
-                acc_step(a, v.x, v.y, c, s);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    float cn = c[q] * cd[q] - s[q] * sd[q];
-                    float sn = c[q] * sd[q] + s[q] * cd[q];
-                    c[q] = cn;
-                    s[q] = sn;
-                }
+                const float2 v = wp[r * LAG_PITCH + j8];
+                drift_step(ai01, aq01, ai23, aq23, v.x, v.y, ph, negzero, one);
             }
         }
+        Acc8 a;
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
         power = acc_power(a);
     }
     P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = power;
@@ -740,7 +769,6 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
     for (int q = 0; q < 4; q++) a.ai[q] = a.aq[q] = 0.0f;
     const bool inside = (start > 0) && (start + SPS <= np);
     float cd[4], sd[4], c[4] = {1.0f, 1.0f, 1.0f, 1.0f}, s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (!shared_tab) tone_seeds(fp, cd, sd);
     if (shared_tab && inside) {                                // the common case, packed like k_sync_lags
         const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
         pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
@@ -772,7 +800,32 @@ __device__ __forceinline__ float4 correlate_symbol(const float *__restrict__ ip,
         }
         a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
         a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
+    } else if (!shared_tab && inside) {                        // drifting candidate, whole window inside the capture: packed recurrence
+        DriftPhasors ph;
+        drift_init(ph, fp);
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
+        const bool aligned = (start & 3) == 0;
+        const float4 *i4 = reinterpret_cast<const float4 *>(ip + (aligned ? start : 0)), *q4 = reinterpret_cast<const float4 *>(qp + (aligned ? start : 0));
+        for (int j4 = 0; j4 < SPS / 4; j4++) {
+            float xs[4], ys[4];
+            if (aligned) {
+                const float4 xi = i4[j4], xq = q4[j4];
+                xs[0] = xi.x; xs[1] = xi.y; xs[2] = xi.z; xs[3] = xi.w;
+                ys[0] = xq.x; ys[1] = xq.y; ys[2] = xq.z; ys[3] = xq.w;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    xs[r] = ip[start + j4 * 4 + r];
+                    ys[r] = qp[start + j4 * 4 + r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) drift_step(ai01, aq01, ai23, aq23, xs[r], ys[r], ph, negzero, one);
+        }
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
     } else {
+        if (!shared_tab) tone_seeds(fp, cd, sd);
         for (int j = 0; j < SPS; j++) {
             int k = start + j;
             float x = 0.0f, y = 0.0f;
