@@ -480,9 +480,22 @@ static int read_counters(wspr_ctx *c) {
     return wait_stream(c);
 }
 
-// every open capture is parked with the Fano workers: sleep until one more has been handed back (`seen`: the count
-// read before the round was planned, so a hand-back in between is not missed)
-// `want` more hand-backs are worth waiting a little longer for (a round costs two host synchronisations whatever its size)
+// (`seen`: the count read before the round was planned, so a hand-back in between is not missed)
+// give the pool up to park_linger_us to hand `want` captures back (counted from `seen`): a round costs two host
+// synchronisations and some twenty launches whatever its size
+static void linger_parked(wspr_ctx *c, int seen, int want) {
+    if (c->park_linger_us <= 0) return;
+    const volatile int *done = c->h_done;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (*done - seen < want) {
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((t1.tv_sec - t0.tv_sec) * 1000000L + (t1.tv_nsec - t0.tv_nsec) / 1000L >= c->park_linger_us) break;
+        if (wait_blocks()) usleep(50);
+        else sched_yield();
+    }
+}
+// every open capture is parked: sleep until at least one has been handed back, then linger for more
 static int wait_parked(wspr_ctx *c, int seen, int want) {
     const volatile int *done = c->h_done;
     for (unsigned spin = 0; *done == seen; spin++) {
@@ -493,16 +506,7 @@ static int wait_parked(wspr_ctx *c, int seen, int want) {
         if (wait_blocks()) usleep(50);
         else sched_yield();
     }
-    if (c->park_linger_us > 0 && want > 1) {
-        timespec t0, t1;
-        clock_gettime(CLOCK_MONOTONIC, &t0);
-        while (*done - seen < want) {
-            clock_gettime(CLOCK_MONOTONIC, &t1);
-            if ((t1.tv_sec - t0.tv_sec) * 1000000L + (t1.tv_nsec - t0.tv_nsec) / 1000L >= c->park_linger_us) break;
-            if (wait_blocks()) usleep(50);
-            else sched_yield();
-        }
-    }
+    if (want > 1) linger_parked(c, seen, want);
     return WSPR_OK;
 }
 
@@ -614,6 +618,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     CK(cudaEventRecord(c->ev0, c->st));
     CK(cudaMemsetAsync(c->stats, 0, 8 * sizeof(int), c->st));
     launch_reset_caps(c->caps, ncap, o.npasses, c->st);
+    bool lingered = false;
     while (ncap > 0) {
         const int seen = *(volatile int *)c->h_done;
         launch_plan(c->caps, c->cands, c->jobs, c->setup_list, c->job_list, c->res_list, c->cnt, ncap, o.npasses, c->st);
@@ -632,6 +637,15 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             if (wait_parked(c, seen, std::min(h.nwait, 64))) return WSPR_ERR_CUDA;
             continue;
         }
+        // a handful of captures ready while many more are with the pool: give those a moment to come back and plan again
+        // (once), rather than running a round of near-empty grids for every capture that trickles in
+        const int ready = h.nsetup + h.njobs + h.nres;
+        if (!lingered && h.nwait > 0 && ready < 8 && ready * 4 < h.nwait) {
+            lingered = true;
+            linger_parked(c, seen, std::min(h.nwait, 16));
+            continue;
+        }
+        lingered = false;
         c->rounds++;
         // captures entering a pass: spectrogram, candidate search, coarse sync (wsprd.c:536-678)
         launch_spectrogram(c->I, c->Q, c->psT, c->setup_list, h.nsetup, p, c->st);
