@@ -148,7 +148,8 @@ double wspr_ctx_last_sync_cells(wspr_ctx *ctx);
  * not converge at once): out8[0] worker warps allowed, [1] SMs set aside for them (0: they share the SMs with the other
  * kernels), [2] housekeeping periods (256 decoder-loop trips) worker warps were alive for, [3] lane-periods with an attempt
  * in the lane (utilisation = [3] / (32 x [2])), [4] attempts decoded to their end, [5] attempts skipped or abandoned,
- * [6] worker warps started.  device -1: the current device; reset != 0 clears the counters. */
+ * [6] worker warps started, [7] the part of [2] spent by overflow workers (section 6b of DESIGN.md).  device -1: the current
+ * device; reset != 0 clears the counters. */
 int wspr_fano_stats(int device, unsigned long long *out8, int reset);
 
 /* the Fano decoder kernel (K5) on caller-supplied soft symbols: n vectors of 162 deinterleaved bytes, the batch / device

@@ -82,6 +82,8 @@ static void host_tables(HostTables &t) {
 //   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
 //                   per SM unpartitioned)
 //   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
+//   WSPR_FANO_OVERFLOW  with a partition: this many extra worker warps may run on the other kernels' SMs (at most
+//                   WSPR_FANO_PER_SM per SM) while at least WSPR_FANO_OVERFLOW_BACKLOG candidates wait for lanes
 //   WSPR_FANO_CTA_WARPS  worker warps per CTA (1, 2 or 4)
 //   WSPR_CARVEOUT_KB  common shared-memory carve-out of every decode kernel (0 = the driver's per-kernel choice)
 // All are read once, when the first context on a device is created.
@@ -90,6 +92,9 @@ static void host_tables(HostTables &t) {
 #endif
 #ifndef WSPR_DEFAULT_CARVEOUT_KB
 #define WSPR_DEFAULT_CARVEOUT_KB 164              // K4's two 47 KB CTAs + two worker warps; measured in profiles/r2_bench_variants.txt
+#endif
+#ifndef WSPR_DEFAULT_FANO_OVERFLOW
+#define WSPR_DEFAULT_FANO_OVERFLOW 0
 #endif
 #ifndef WSPR_DEFAULT_FANO_SHARE
 #define WSPR_DEFAULT_FANO_SHARE 0
@@ -109,6 +114,7 @@ constexpr int NFANO_STREAMS = 4;
 struct FanoService {
     int device = -1;
     int fano_sms = 0, pool = 0, total_sms = 0, cta_warps = 1;
+    int pool2 = 0;                                 // overflow worker warps on the other kernels' SMs (partition only)
     bool partitioned = false;
     bool shared_bulk = false;                      // the other kernels may use the pool's SMs as well (WSPR_FANO_SHARE)
     CUgreenCtx g_fano = nullptr, g_bulk = nullptr;
@@ -182,7 +188,11 @@ static FanoService *fano_service(int device) {
     FanoQueue h;
     memset(&h, 0, sizeof h);
     h.pool = s->pool;
-    h.per_sm = env_int("WSPR_FANO_PER_SM", s->partitioned ? 0 : WSPR_DEFAULT_FANO_PER_SM);
+    // with a partition: the per-SM limit is for the overflow workers (the partition's SMs hold as many as fit)
+    s->pool2 = s->partitioned && !s->shared_bulk ? std::max(0, env_int("WSPR_FANO_OVERFLOW", WSPR_DEFAULT_FANO_OVERFLOW)) : 0;
+    h.pool2 = s->pool2;
+    h.ovf_backlog = std::max(1, env_int("WSPR_FANO_OVERFLOW_BACKLOG", 8));
+    h.per_sm = env_int("WSPR_FANO_PER_SM", (s->partitioned && s->pool2 == 0) ? 0 : WSPR_DEFAULT_FANO_PER_SM);
     h.mask = FANO_RING - 1;
     if (cudaMalloc((void **)&s->ring, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||
         cudaMemset(s->ring, 0, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||
@@ -231,6 +241,7 @@ struct wspr_ctx {
     FanoService *svc = nullptr;
     cudaStream_t st = nullptr;
     cudaStream_t fano_st[NFANO_STREAMS] = {nullptr};   // worker warps are launched here (the pool's SM partition, if any)
+    cudaStream_t ovf_st[NFANO_STREAMS] = {nullptr};    // overflow worker warps (the other kernels' SMs)
     int fano_rr = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_wait = nullptr;   // blocking-sync event: host threads sleep instead of spinning while the GPU works
@@ -284,6 +295,8 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
     }
     for (cudaStream_t s : c->fano_st)
         if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : c->ovf_st)
+        if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -311,6 +324,8 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     if (!c->svc) return fail(WSPR_ERR_CUDA, "Fano service set-up failed", cudaGetLastError());
     CK(service_stream(c->svc, false, &c->st));
     for (cudaStream_t &s : c->fano_st) CK(service_stream(c->svc, true, &s));
+    if (c->svc->pool2 > 0)
+        for (cudaStream_t &s : c->ovf_st) CK(service_stream(c->svc, false, &s));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
@@ -682,7 +697,12 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];
                 CK(cudaStreamWaitEvent(fs, c->ev_fano, 0));
                 const int attempts = ndefer * (p.quickmode ? 1 : NJIT);
-                launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), c->svc->cta_warps, p, fs);
+                launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), c->svc->cta_warps, false, p, fs);
+                if (c->svc->pool2 > 0) {
+                    cudaStream_t os = c->ovf_st[c->fano_rr % NFANO_STREAMS];
+                    CK(cudaStreamWaitEvent(os, c->ev_fano, 0));
+                    launch_fano_workers(c->svc->queue, std::min(c->svc->pool2, (attempts + 31) / 32), 1, true, p, os);
+                }
             }
         }
         // in-order tail of the candidate loop for everything that finished, then the subtractions (wsprd.c:768-822)
@@ -746,8 +766,8 @@ extern "C" int wspr_fano_stats(int device, unsigned long long *out8, int reset) 
     out8[4] = h.st_attempts;
     out8[5] = h.st_dropped;
     out8[6] = h.st_warps;
-    out8[7] = 0;
-    if (reset) CK(cudaMemset(&s->queue->st_warp_periods, 0, 5 * sizeof(unsigned long long)));
+    out8[7] = h.st_ovf_warp_periods;
+    if (reset) CK(cudaMemset(&s->queue->st_warp_periods, 0, 6 * sizeof(unsigned long long)));
     return WSPR_OK;
 }
 

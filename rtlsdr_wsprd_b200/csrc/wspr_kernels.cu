@@ -1281,7 +1281,11 @@ struct FanoQueueFeed {
     FanoQueue *q;
     ChainScratch *cs;
     int idt;
+    bool overflow;                                             // an overflow worker: takes work only while a backlog exists
     unsigned periods, busy_periods, attempts, dropped;         // statistics of this lane
+    __device__ bool backlog() const {
+        return (int)(*(volatile unsigned *)&q->tail - *(volatile unsigned *)&q->head1) >= *(volatile int *)&q->ovf_backlog;
+    }
     __device__ void period(bool active) {
         periods++;
         busy_periods += active ? 1u : 0u;
@@ -1289,6 +1293,7 @@ struct FanoQueueFeed {
     __device__ const unsigned char *next(unsigned &stop_after) {
         stop_after = 0;
         for (;;) {
+            if (overflow && !backlog()) return nullptr;
             const unsigned tail = *(volatile unsigned *)&q->tail;
             unsigned h = *(volatile unsigned *)&q->head0;
             if (h != tail) {                                   // attempt 0 of the next candidate nobody has started
@@ -1348,22 +1353,28 @@ struct FanoQueueFeed {
 // the place back if there is something to do -- so work is never stranded, and nobody ever waits for work.
 // A CTA carries blockDim.x / 32 worker warps, completely independent of each other (no CTA barrier): with more than one the
 // warps of a CTA sit on different schedulers of their SM, which single-warp CTAs leave to chance.
-__global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles) {
+__global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles, int overflow) {
     extern __shared__ __align__(16) unsigned char fano_smem_all[];
     unsigned char *fano_smem = fano_smem_all + (size_t)(threadIdx.x >> 5) * FANO_WARP_SMEM_BYTES;
     const unsigned lane = threadIdx.x & 31u;
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     smid &= 255u;
+    int *active = overflow ? &q->active2 : &q->active;
+    const volatile int *pool = overflow ? &q->pool2 : &q->pool;
+    FanoQueueFeed feed{q, nullptr, 0, overflow != 0, 0u, 0u, 0u, 0u};
+    const int per_sm = *(volatile int *)&q->per_sm;
     int mine = 0;
     if (lane == 0) {
-        const int per_sm = *(volatile int *)&q->per_sm;
-        mine = per_sm <= 0 || atomicAdd(&q->sm_workers[smid], 1) < per_sm;     // (this SM has its share of workers: leave)
-        if (!mine) atomicSub(&q->sm_workers[smid], 1);
+        mine = !overflow || feed.backlog();
+        if (mine && per_sm > 0) {                              // (this SM has its share of workers: leave)
+            mine = atomicAdd(&q->sm_workers[smid], 1) < per_sm;
+            if (!mine) atomicSub(&q->sm_workers[smid], 1);
+        }
         if (mine) {
-            mine = atomicAdd(&q->active, 1) < *(volatile int *)&q->pool;
+            mine = atomicAdd(active, 1) < *pool;
             if (!mine) {
-                atomicSub(&q->active, 1);
+                atomicSub(active, 1);
                 if (per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
             }
         }
@@ -1371,17 +1382,17 @@ __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q,
     mine = __shfl_sync(0xffffffffu, mine, 0);
     if (!mine) return;
     EXP_WORKER(1);
-    FanoQueueFeed feed{q, nullptr, 0, 0u, 0u, 0u, 0u};
     while (mine) {
         fano_run<false>(feed, FanoSmem::at(fano_smem), &c_mettab[0][0], delta, maxcycles);
         mine = 0;
         if (lane == 0) {
-            atomicSub(&q->active, 1);
+            atomicSub(active, 1);
             __threadfence();
             const unsigned tail = *(volatile unsigned *)&q->tail;
-            if (*(volatile unsigned *)&q->head0 != tail || *(volatile unsigned *)&q->head1 != tail) {
-                mine = atomicAdd(&q->active, 1) < *(volatile int *)&q->pool;
-                if (!mine) atomicSub(&q->active, 1);
+            const bool pending = overflow ? feed.backlog() : (*(volatile unsigned *)&q->head0 != tail || *(volatile unsigned *)&q->head1 != tail);
+            if (pending) {
+                mine = atomicAdd(active, 1) < *pool;
+                if (!mine) atomicSub(active, 1);
             }
         }
         mine = __shfl_sync(0xffffffffu, mine, 0);
@@ -1390,8 +1401,9 @@ __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q,
                    drop = __reduce_add_sync(0xffffffffu, feed.dropped);
     EXP_WORKER(-1);
     if (lane == 0) {
-        if (*(volatile int *)&q->per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
+        if (per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
         atomicAdd(&q->st_warp_periods, (unsigned long long)feed.periods);
+        if (overflow) atomicAdd(&q->st_ovf_warp_periods, (unsigned long long)feed.periods);
         atomicAdd(&q->st_lane_periods, (unsigned long long)busy);
         atomicAdd(&q->st_attempts, (unsigned long long)att);
         atomicAdd(&q->st_dropped, (unsigned long long)drop);
@@ -1412,7 +1424,7 @@ void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *a
 }
 
 int fano_warp_smem_bytes() { return FANO_WARP_SMEM_BYTES; }
-void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, const DecodeParams &p, cudaStream_t st) {
+void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, bool overflow, const DecodeParams &p, cudaStream_t st) {
     if (nwarps <= 0) return;
     cta_warps = cta_warps == 2 ? 2 : (cta_warps == 4 ? 4 : 1);
     unsigned maxcycles = p.maxcycles;
@@ -1422,8 +1434,8 @@ void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, const Deco
     static const unsigned dbg = [] { const char *e = getenv("WSPR_DEBUG_CHAIN_MAXCYCLES"); return e ? (unsigned)atoi(e) : 0u; }();
     if (dbg) maxcycles = dbg;
 #endif
-    k_fano_workers<<<(nwarps + cta_warps - 1) / cta_warps, 32 * cta_warps, (size_t)cta_warps * FANO_WARP_SMEM_BYTES, st>>>(queue, p.delta,
-                                                                                                                        maxcycles);
+    k_fano_workers<<<(nwarps + cta_warps - 1) / cta_warps, 32 * cta_warps, (size_t)cta_warps * FANO_WARP_SMEM_BYTES, st>>>(
+        queue, p.delta, maxcycles, overflow ? 1 : 0);
     LAUNCHED();
 }
 

@@ -153,10 +153,14 @@ struct FanoQueue {
     unsigned mask;      // capacity - 1 (power of two)
     int overflow;       // a producer found the ring full (the decode reports an error)
     int per_sm;         // worker warps allowed on one SM (0: no limit)
+    // overflow workers (only with an SM partition for the pool): warps that share the SMs of the other kernels and take work
+    // only while at least `ovf_backlog` candidates are waiting for lanes -- they absorb the bursts a round produces, the
+    // partition carries the base load
+    int active2, pool2, ovf_backlog;
     FanoQueueEntry *ring;
     // statistics (wspr_fano_stats): housekeeping periods (256 loop trips) worker warps were alive for / their lanes had an
     // attempt in, attempts decoded to the end, attempts skipped or abandoned, worker warps started
-    unsigned long long st_warp_periods, st_lane_periods, st_attempts, st_dropped, st_warps;
+    unsigned long long st_warp_periods, st_lane_periods, st_attempts, st_dropped, st_warps, st_ovf_warp_periods;
     int sm_workers[256];
 };
 
@@ -199,7 +203,7 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
                      ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
                      cudaStream_t st);
-void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, const DecodeParams &p, cudaStream_t st);
+void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, bool overflow, const DecodeParams &p, cudaStream_t st);
 void init_kernel_attributes(int carveout_kb);   // per device: opt-in to > 48 KB of dynamic shared memory, common carve-out
 int fano_warp_smem_bytes();                  // shared memory one worker warp holds
 void launch_resolve(Job *jobs, CapState *caps, Spot *spots, const int *res_list, int nres_max, int *sub_list, Counters *cnt,

@@ -373,7 +373,8 @@ def fano_pool_stats(device=-1, reset=False):
     _check(library().wspr_fano_stats(int(device), out, int(bool(reset))), "wspr_fano_stats")
     v = [int(x) for x in out]
     return {"pool_warps": v[0], "fano_sms": v[1], "warp_periods": v[2], "lane_utilisation": round(v[3] / (32.0 * v[2]), 4) if v[2] else None,
-            "attempts_run": v[4], "attempts_dropped": v[5], "worker_warps_started": v[6]}
+            "attempts_run": v[4], "attempts_dropped": v[5], "worker_warps_started": v[6],
+            "overflow_share": round(v[7] / v[2], 4) if v[2] else None}
 
 
 def decimate_batch(raw, n_iq=None, max_out=NSAMP, device=-1):

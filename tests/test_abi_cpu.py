@@ -223,10 +223,12 @@ def test_packed_products_and_sums_are_not_contracted():
             cur = m.group(1)
         elif cur and "FFMA2" in line:
             count[cur] = count.get(cur, 0) + 1
-    # packed multiply-accumulates per sample (4 tones x {i,q} x 2 products / 2 lanes = 8; low-pass: 4 outputs) x samples
-    # (taps) in the unrolled loop body x 2 instructions each
-    expected = {"k_sync_lagsE": 8 * 16 * 2, "k_sync_freqsE": 8 * 8 * 2, "k_sync_freqs_sharedE": 8 * 8 * 2, "k_jitter_softE": 8 * 8 * 2,
-                "k_sync_genericE": 8 * 8 * 2, "k_sub_lpfI": 4 * 8 * 2}
+    # table path: packed multiply-accumulates per sample (4 tones x {i,q} x 2 products / 2 lanes = 8; low-pass: 4 outputs) x
+    # samples (taps) in the unrolled loop body x 2 instructions each.  Drifting candidates advance their phasors in
+    # registers: 28 FFMA2 per sample (16 for the sums + 8 products and 4 sums of the recurrence) x the samples of the
+    # unrolled body (nvcc 12.9 unrolls the 8-sample K4 body four times, the 4-sample bodies twice).
+    expected = {"k_sync_lagsE": 8 * 16 * 2 + 32 * 28, "k_sync_freqsE": 8 * 8 * 2 + 8 * 28, "k_sync_freqs_sharedE": 8 * 8 * 2,
+                "k_jitter_softE": 8 * 8 * 2 + 8 * 28, "k_sync_genericE": 8 * 8 * 2 + 16 * 28, "k_sub_lpfI": 4 * 8 * 2}
     for name, n in expected.items():                     # (mangled names: the suffix keeps k_sync_freqs and ..._shared apart)
         got = sum(v for k, v in count.items() if name in k)
         assert got == n, (name, got, n)
