@@ -108,7 +108,8 @@ static void host_tables(HostTables &t) {
 #ifndef WSPR_DEFAULT_FANO_POOL_PER_SM
 #define WSPR_DEFAULT_FANO_POOL_PER_SM 2
 #endif
-constexpr int FANO_RING = 1 << 16;                 // candidates the queue can hold
+constexpr int EXACT_SIZING_MIN_JOBS = 64;
+constexpr int FANO_RING = 1 << 18;                 // candidates the queue can hold (64 contexts of 4096 captures, all parked)
 constexpr int NFANO_STREAMS = 4;
 
 struct FanoService {
@@ -686,17 +687,23 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
             launch_sync_freqs(c->I, c->Q, c->jobs, c->job_list, h.njobs, c->P0, c->P1, c->tabs, c->att0, p, c->st);
             launch_fano_round(c->att0, c->job_list, h.njobs, p, c->st);
             launch_collect(c->jobs, c->att0, c->caps, c->job_list, h.njobs, c->res_list, c->defer_list, c->cnt, p, c->st);
-            if (read_counters(c)) return WSPR_ERR_CUDA;
-            const int ndefer = c->h_cnt->ndefer;
-            nres_max = c->h_cnt->nres;
-            if (ndefer > 0) {                                 // finish them off the critical path
-                c->deferred += ndefer;
-                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer, c->scratch, c->tabs, c->stats, c->h_done,
-                                c->svc->queue, p, c->st);
+            // big rounds: read the round's counters back so that the grids below are sized exactly; small ones (the
+            // straggler rounds, nine tenths of all rounds) size them from the job count and let the kernels read the
+            // counts on the device -- one host synchronisation per round instead of two
+            int ndefer_max = h.njobs;
+            nres_max = h.nres + h.njobs;
+            if (h.njobs >= EXACT_SIZING_MIN_JOBS) {
+                if (read_counters(c)) return WSPR_ERR_CUDA;
+                ndefer_max = c->h_cnt->ndefer;
+                nres_max = c->h_cnt->nres;
+            }
+            if (ndefer_max > 0) {                             // finish them off the critical path
+                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer_max, c->cnt, c->scratch, c->tabs, c->stats,
+                                c->h_done, c->svc->queue, p, c->st);
                 CK(cudaEventRecord(c->ev_fano, c->st));
                 cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];
                 CK(cudaStreamWaitEvent(fs, c->ev_fano, 0));
-                const int attempts = ndefer * (p.quickmode ? 1 : NJIT);
+                const int attempts = ndefer_max * (p.quickmode ? 1 : NJIT);
                 launch_fano_workers(c->svc->queue, std::min(c->svc->pool, (attempts + 31) / 32), c->svc->cta_warps, false, p, fs);
                 if (c->svc->pool2 > 0) {
                     cudaStream_t os = c->ovf_st[c->fano_rr % NFANO_STREAMS];
@@ -716,6 +723,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     CK(cudaEventRecord(c->ev1, c->st));
     if (wait_stream(c)) return WSPR_ERR_CUDA;
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    c->deferred = c->h_stats[4];
     {
         int overflow = 0;
         CK(cudaMemcpy(&overflow, &c->svc->queue->overflow, sizeof(int), cudaMemcpyDeviceToHost));

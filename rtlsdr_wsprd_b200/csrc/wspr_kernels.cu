@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const f
         a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
         power = acc_power(a);
     }
-    P0[((size_t)blockIdx.x * MAXLAGS + lagidx) * NSYM + sym] = power;
+    P0[((size_t)blockIdx.x * NSYM + sym) * MAXLAGS + lagidx] = power;    // [job][symbol][lag]: consecutive lanes, consecutive words
     EXP_STOP();
 }
 
@@ -718,10 +718,10 @@ __global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const i
     const int t = threadIdx.x;
     float v = CUDART_NAN_F;
     if (t < nlags) {
-        const float4 *p = P0 + ((size_t)blockIdx.x * MAXLAGS + t) * NSYM;
+        const float4 *p = P0 + (size_t)blockIdx.x * NSYM * MAXLAGS + t;   // lane t = lag t: the lanes read consecutive words
         float ss = 0.0f, totp = 0.0f;
         for (int i = 0; i < NSYM; i++) {
-            float4 q = p[i];
+            float4 q = p[(size_t)i * MAXLAGS];
             totp = totp + q.x + q.y + q.z + q.w;
             float cmet = (q.y + q.w) - (q.x + q.z);
             ss = sync_bit(i) ? ss + cmet : ss - cmet;
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(192) k_sync_freqs(const float *__restrict__ I,
     const int fi = blockIdx.y, t = threadIdx.x;
     if (fi == 2 && job.lbest >= 0) {       // the centre hypothesis repeats the winning cell row of the lag search exactly
         if (t < NSYM)
-            P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = P0[((size_t)blockIdx.x * MAXLAGS + job.lbest) * NSYM + t];
+            P1[((size_t)blockIdx.x * NFREQ1 + fi) * NSYM + t] = P0[((size_t)blockIdx.x * NSYM + t) * MAXLAGS + job.lbest];
         return;
     }
     const bool shared_tab = (job.drift == 0.0f);
@@ -1179,13 +1179,17 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I, const float *__restrict__ Q,
                                                      Job *__restrict__ jobs, const Attempt *__restrict__ att0,
                                                      CapState *__restrict__ caps, const int *__restrict__ defer_list,
-                                                     ChainScratch *__restrict__ scratch, const float4 *__restrict__ tabs,
+                                                     const Counters *__restrict__ cnt, ChainScratch *__restrict__ scratch,
+                                                     const float4 *__restrict__ tabs,
                                                      int *__restrict__ stats, int *__restrict__ host_done, int nattempts,
                                                      int np, int stride, float minrms, int symfac, pk2 negzero, pk2 one) {
     __shared__ float4 tab[2 * SPS];
     __shared__ float4 P[NSYM];
     __shared__ SoftScratch soft;
-    const int e = blockIdx.x, idt = blockIdx.y, t = threadIdx.x;
+    const int idt = blockIdx.y, t = threadIdx.x;
+    const int n = cnt->ndefer;                                 // (the grid is sized from an upper bound; see launch_deferred)
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    __syncthreads();                                           // the previous candidate's tables are no longer in use
     const int cap = defer_list[e];
     const Job &job = jobs[cap];
     ChainScratch &cs = scratch[cap];
@@ -1203,7 +1207,7 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
             cs.stats = stats;
             cs.host_done = host_done;
         }
-        return;
+        continue;
     }
     int ii = (idt + 1) / 2;
     if (idt % 2 == 1) ii = -ii;
@@ -1227,12 +1231,17 @@ __global__ void __launch_bounds__(192) k_jitter_soft(const float *__restrict__ I
             cs.ok[idt] = cs.unfinished[idt] = 0;
         }
     }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_fano_enqueue(FanoQueue *__restrict__ q, ChainScratch *__restrict__ scratch,
-                                                      const int *__restrict__ defer_list, int n) {
+                                                      const int *__restrict__ defer_list, const Counters *__restrict__ cnt,
+                                                      int *__restrict__ stats) {
     __shared__ unsigned s_base;
+    const int n = cnt->ndefer;
+    if (n <= 0) return;
     if (threadIdx.x == 0) {
+        atomicAdd(stats + 4, n);                               // candidates parked during this decode
         const unsigned base = atomicAdd(&q->tail, (unsigned)n);
         const unsigned h0 = *(volatile unsigned *)&q->head0, h1 = *(volatile unsigned *)&q->head1;
         const unsigned oldest = (int)(h0 - h1) < 0 ? h0 : h1;
@@ -1411,15 +1420,17 @@ __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q,
     }
 }
 
-void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
-                     cudaStream_t st) {
-    if (n <= 0) return;
+// n_max: upper bound of the candidates parked by this round (the exact number is cnt->ndefer, on the device)
+void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n_max,
+                     const Counters *cnt, ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue,
+                     const DecodeParams &p, cudaStream_t st) {
+    if (n_max <= 0) return;
     const int nattempts = p.quickmode ? 1 : NJIT;
-    k_jitter_soft<<<dim3(n, nattempts), 192, 0, st>>>(I, Q, jobs, att0, caps, defer_list, scratch, tabs, stats, host_done, nattempts,
-                                                      p.np, p.stride, p.minrms, p.symfac, PK_NEGZERO, PK_ONE);
+    k_jitter_soft<<<dim3(std::min(n_max, 256), nattempts), 192, 0, st>>>(I, Q, jobs, att0, caps, defer_list, cnt, scratch, tabs, stats,
+                                                                         host_done, nattempts, p.np, p.stride, p.minrms, p.symfac,
+                                                                         PK_NEGZERO, PK_ONE);
     LAUNCHED();
-    k_fano_enqueue<<<1, 256, 0, st>>>(queue, scratch, defer_list, n);
+    k_fano_enqueue<<<1, 256, 0, st>>>(queue, scratch, defer_list, cnt, stats);
     LAUNCHED();
 }
 

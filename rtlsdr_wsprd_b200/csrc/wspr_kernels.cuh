@@ -200,9 +200,9 @@ void launch_collect(Job *jobs, const Attempt *att0, CapState *caps, const int *j
 // parked candidates (wsprd.c:741-766): soft symbols of the jittered attempts into scratch[capture], then all attempts of the
 // n candidates into the device queue; launch_fano_workers starts up to `nwarps` worker warps on `st` (they leave at once
 // when the pool is already complete, and when the queue runs dry)
-void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n,
-                     ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue, const DecodeParams &p,
-                     cudaStream_t st);
+void launch_deferred(const float *I, const float *Q, Job *jobs, const Attempt *att0, CapState *caps, const int *defer_list, int n_max,
+                     const Counters *cnt, ChainScratch *scratch, const float4 *tabs, int *stats, int *host_done, FanoQueue *queue,
+                     const DecodeParams &p, cudaStream_t st);
 void launch_fano_workers(FanoQueue *queue, int nwarps, int cta_warps, bool overflow, const DecodeParams &p, cudaStream_t st);
 void init_kernel_attributes(int carveout_kb);   // per device: opt-in to > 48 KB of dynamic shared memory, common carve-out
 int fano_warp_smem_bytes();                  // shared memory one worker warp holds
