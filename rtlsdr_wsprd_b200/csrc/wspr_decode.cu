@@ -75,18 +75,19 @@ static void host_tables(HostTables &t) {
 // of worker warps per GPU, fed from a device-side queue that every context of the process pushes to (wspr_kernels.cu,
 // k_fano_workers).  Optionally the pool runs on its own SM partition (CUDA green contexts through the driver API; libcuda is
 // not linked, the entry points come from cudaGetDriverEntryPoint): the workers then never share an SM -- its issue slots, its
-// shared-memory carve-out -- with the bulk kernels, which get the remaining SMs.
+// shared-memory carve-out -- with the bulk kernels, which get the remaining SMs.  Every placement other than the default
+// (two one-warp workers per SM, no partition, one common 164 KB carve-out) measured slower (profiles/r2_bench_variants.txt),
+// so only two sizing knobs are read by the product library, once, when the first context on a device is created:
+//   WSPR_FANO_POOL    worker warps alive at any time (default 2 per SM)
+//   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit; default 2)
+// and the alternatives can be selected at run time only in the experiment build (make exp):
 //   WSPR_FANO_SMS   SMs set aside for the pool (even; 0 = no partition, workers and bulk kernels share every SM)
 //   WSPR_FANO_SHARE 1: the pool is confined to its WSPR_FANO_SMS SMs but the other kernels run on ALL SMs (they use whatever
 //                   the workers leave of those SMs); 0: the other kernels keep off the pool's SMs
-//   WSPR_FANO_POOL  worker warps (default: 7 per partition SM, the number that fit its shared memory; WSPR_DEFAULT_FANO_POOL_PER_SM
-//                   per SM unpartitioned)
-//   WSPR_FANO_PER_SM  worker warps allowed on one SM (0 = no limit)
 //   WSPR_FANO_OVERFLOW  with a partition: this many extra worker warps may run on the other kernels' SMs (at most
 //                   WSPR_FANO_PER_SM per SM) while at least WSPR_FANO_OVERFLOW_BACKLOG candidates wait for lanes
 //   WSPR_FANO_CTA_WARPS  worker warps per CTA (1, 2 or 4)
 //   WSPR_CARVEOUT_KB  common shared-memory carve-out of every decode kernel (0 = the driver's per-kernel choice)
-// All are read once, when the first context on a device is created.
 #ifndef WSPR_DEFAULT_FANO_SMS
 #define WSPR_DEFAULT_FANO_SMS 0
 #endif
@@ -140,6 +141,16 @@ static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e && *e ? atoi(e) : dflt;
 }
+// placement alternatives that were measured and rejected (profiles/r2_bench_variants.txt): selectable at run time only in
+// the experiment build (make exp), the product library runs its compiled-in defaults
+static int exp_int(const char *name, int dflt) {
+#ifdef WSPR_EXPERIMENTS
+    return env_int(name, dflt);
+#else
+    (void)name;
+    return dflt;
+#endif
+}
 
 // SM partition: `want` SMs for the Fano pool, the rest for everything else
 static bool fano_partition(FanoService *s, int want) {
@@ -174,25 +185,25 @@ static FanoService *fano_service(int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return nullptr; }
     s->total_sms = prop.multiProcessorCount;
-    init_kernel_attributes(env_int("WSPR_CARVEOUT_KB", WSPR_DEFAULT_CARVEOUT_KB));
-    const int want = env_int("WSPR_FANO_SMS", WSPR_DEFAULT_FANO_SMS);
+    init_kernel_attributes(exp_int("WSPR_CARVEOUT_KB", WSPR_DEFAULT_CARVEOUT_KB));
+    const int want = exp_int("WSPR_FANO_SMS", WSPR_DEFAULT_FANO_SMS);
     if (want > 0 && want < s->total_sms) {
         s->partitioned = fano_partition(s, want);
         if (!s->partitioned) s->note = "SM partition unavailable (green contexts): Fano workers share the SMs";
     }
     if (!s->partitioned) s->fano_sms = 0;
-    s->shared_bulk = s->partitioned && env_int("WSPR_FANO_SHARE", WSPR_DEFAULT_FANO_SHARE) != 0;
+    s->shared_bulk = s->partitioned && exp_int("WSPR_FANO_SHARE", WSPR_DEFAULT_FANO_SHARE) != 0;
     const int per_sm = (228 * 1024) / (fano_warp_smem_bytes() + 1024);
     s->pool = env_int("WSPR_FANO_POOL", s->partitioned ? s->fano_sms * per_sm : s->total_sms * WSPR_DEFAULT_FANO_POOL_PER_SM);
     if (s->pool < 1) s->pool = 1;
-    s->cta_warps = env_int("WSPR_FANO_CTA_WARPS", WSPR_DEFAULT_FANO_CTA_WARPS);
+    s->cta_warps = exp_int("WSPR_FANO_CTA_WARPS", WSPR_DEFAULT_FANO_CTA_WARPS);
     FanoQueue h;
     memset(&h, 0, sizeof h);
     h.pool = s->pool;
     // with a partition: the per-SM limit is for the overflow workers (the partition's SMs hold as many as fit)
-    s->pool2 = s->partitioned && !s->shared_bulk ? std::max(0, env_int("WSPR_FANO_OVERFLOW", WSPR_DEFAULT_FANO_OVERFLOW)) : 0;
+    s->pool2 = s->partitioned && !s->shared_bulk ? std::max(0, exp_int("WSPR_FANO_OVERFLOW", WSPR_DEFAULT_FANO_OVERFLOW)) : 0;
     h.pool2 = s->pool2;
-    h.ovf_backlog = std::max(1, env_int("WSPR_FANO_OVERFLOW_BACKLOG", 8));
+    h.ovf_backlog = std::max(1, exp_int("WSPR_FANO_OVERFLOW_BACKLOG", 8));
     h.per_sm = env_int("WSPR_FANO_PER_SM", (s->partitioned && s->pool2 == 0) ? 0 : WSPR_DEFAULT_FANO_PER_SM);
     h.mask = FANO_RING - 1;
     if (cudaMalloc((void **)&s->ring, (size_t)FANO_RING * sizeof(FanoQueueEntry)) != cudaSuccess ||

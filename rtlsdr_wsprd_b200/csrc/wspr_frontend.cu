@@ -358,7 +358,11 @@ void launch_decimate(const uint8_t *raw, size_t n_iq, int nstreams, size_t strea
     if (nstreams <= 0 || max_out <= 0) return;
     upload_fir();
     if (nblk > 0) {
+#ifdef WSPR_EXPERIMENTS
         static const bool bulk = [] { const char *e = getenv("WSPR_K0_BULK"); return e && e[0] == '1'; }();   // load-path A/B
+#else
+        constexpr bool bulk = false;                   // (1 % slower than plain vector loads, profiles/r2_k0_bulk_ab.txt)
+#endif
         if (bulk) {
             static bool attr[64] = {false};
             int dev = 0;

@@ -216,19 +216,30 @@ def test_packed_products_and_sums_are_not_contracted():
         sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
     except (OSError, subprocess.CalledProcessError):
         pytest.skip("cuobjdump not available")
-    count, cur = {}, None
+    count, lds64, lds128, cur = {}, {}, {}, None
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = m.group(1)
-        elif cur and "FFMA2" in line:
-            count[cur] = count.get(cur, 0) + 1
+        elif cur:
+            for key, tab in (("FFMA2", count), ("LDS.64", lds64), ("LDS.128", lds128)):
+                if key in line:
+                    tab[cur] = tab.get(cur, 0) + 1
     # table path: packed multiply-accumulates per sample (4 tones x {i,q} x 2 products / 2 lanes = 8; low-pass: 4 outputs) x
     # samples (taps) in the unrolled loop body x 2 instructions each.  Drifting candidates advance their phasors in
     # registers: 28 FFMA2 per sample (16 for the sums + 8 products and 4 sums of the recurrence) x the samples of the
-    # unrolled body (nvcc 12.9 unrolls the 8-sample K4 body four times, the 4-sample bodies twice).
-    expected = {"k_sync_lagsE": 8 * 16 * 2 + 32 * 28, "k_sync_freqsE": 8 * 8 * 2 + 8 * 28, "k_sync_freqs_sharedE": 8 * 8 * 2,
+    # unrolled body (nvcc 12.9 unrolls the 4-sample bodies twice).
+    expected = {"k_sync_freqsE": 8 * 8 * 2 + 8 * 28, "k_sync_freqs_sharedE": 8 * 8 * 2,
                 "k_jitter_softE": 8 * 8 * 2 + 8 * 28, "k_sync_genericE": 8 * 8 * 2 + 16 * 28, "k_sub_lpfI": 4 * 8 * 2}
     for name, n in expected.items():                     # (mangled names: the suffix keeps k_sync_freqs and ..._shared apart)
         got = sum(v for k, v in count.items() if name in k)
         assert got == n, (name, got, n)
+    # K4 reads its samples from shared memory, one 8-byte load per sample in either path plus two 16-byte table loads per
+    # sample in the table path, which makes the check independent of how far the compiler unrolls or peels the loops:
+    # 16 FFMA2 per table-path sample, 28 per drift-path sample.
+    k4 = [k for k in count if "k_sync_lagsE" in k]
+    assert len(k4) == 1
+    table_samples = lds128[k4[0]] // 2
+    drift_samples = lds64[k4[0]] - table_samples
+    assert table_samples > 0 and drift_samples > 0
+    assert count[k4[0]] == 16 * table_samples + 28 * drift_samples, (count[k4[0]], table_samples, drift_samples)
