@@ -582,14 +582,10 @@ __device__ __forceinline__ void drift_step(pk2 &ai01, pk2 &aq01, pk2 &ai23, pk2 
 #define WSPR_K4_SYMS 18                                    // (build-time knobs for A/B measurements of the CTA shape)
 #define WSPR_K4_MINB 2
 #endif
-#ifndef WSPR_K4_WARPS
-#define WSPR_K4_WARPS 0                                    // 0: one warp per group of 32 cells; n: n warps claim the groups from a counter
-#endif
 constexpr int SYMS_PER_CTA = WSPR_K4_SYMS;                 // 162 = 9 x 18
 constexpr int LAG_WIN = SYMS_PER_CTA * SPS + SPS;          // 4864 samples cover every lag of the group
 constexpr int LAG_PITCH = LAG_WIN / 8 + 1;                 // 609
-constexpr int LAG_TASKS = (MAXLAGS * SYMS_PER_CTA + 31) / 32;          // 19 groups of 32 cells
-constexpr int LAG_THREADS = 32 * (WSPR_K4_WARPS ? WSPR_K4_WARPS : LAG_TASKS);   // 608 in the one-warp-per-group form
+constexpr int LAG_THREADS = (MAXLAGS * SYMS_PER_CTA + 31) / 32 * 32;   // 608
 
 // threads 0..3 run the phasor recurrences (:174-188), one tone each.  Caller synchronises.
 __device__ __forceinline__ void build_tables(float fp, float4 *tab, int t) {
@@ -644,51 +640,6 @@ __device__ __forceinline__ void load_tables(float4 *tab, const float4 *__restric
     for (int m = t; m < 2 * SPS; m += nthreads) tab[m] = g[m];
 }
 
-// one (symbol, lag) cell of the CTA's group: cell q = lag + nlags * symbol
-__device__ __forceinline__ void lag_cell(int q, int g, int job_slot, const float2 *win, const float4 *tab, bool shared_tab, float f0,
-                                         float drift, int lagstep, int nlags, float4 *__restrict__ P0, pk2 negzero, pk2 one) {
-    const int sym_local = q / nlags, lagidx = q - sym_local * nlags;
-    const int sym = g * SYMS_PER_CTA + sym_local;
-    if (sym_local >= SYMS_PER_CTA || sym >= NSYM) return;
-    const int off = lagidx * lagstep + sym_local * SPS;     // window-relative start of this cell (multiple of 8)
-    const float2 *wp = win + (off >> 3);
-    pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
-    if (shared_tab) {
-        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
-#pragma unroll 2
-        for (int j8 = 0; j8 < SPS / 8; j8++) {
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const float2 v = wp[r * LAG_PITCH + j8];
-                const pk2 x = pk_make(v.x, v.x), y = pk_make(v.y, v.y), n = pk_make(-v.x, -v.x);
-                const ulonglong2 w01 = tp[j8 * 8 + r], w23 = tp[SPS + j8 * 8 + r];   // .x = (c,c'), .y = (s,s')
-                ai01 = pk_add(pk_add(ai01, pk_mul(x, w01.x, negzero), one), pk_mul(y, w01.y, negzero), one);
-                aq01 = pk_add(pk_add(aq01, pk_mul(n, w01.y, negzero), one), pk_mul(y, w01.x, negzero), one);
-                ai23 = pk_add(pk_add(ai23, pk_mul(x, w23.x, negzero), one), pk_mul(y, w23.y, negzero), one);
-                aq23 = pk_add(pk_add(aq23, pk_mul(n, w23.y, negzero), one), pk_mul(y, w23.x, negzero), one);
-            }
-        }
-    } else {
-        DriftPhasors ph;
-        drift_init(ph, symbol_freq(f0, drift, sym));
-        for (int j8 = 0; j8 < SPS / 8; j8++) {
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const float2 v = wp[r * LAG_PITCH + j8];
-                drift_step(ai01, aq01, ai23, aq23, v.x, v.y, ph, negzero, one);
-            }
-        }
-    }
-    Acc8 a;
-    a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
-    a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
-    P0[((size_t)job_slot * NSYM + sym) * MAXLAGS + lagidx] = acc_power(a);   // [job][symbol][lag]: consecutive lanes, consecutive words
-}
-
-// A CTA's shared memory and slots are released when its LAST warp ends and its warps are dealt evenly to the SM's four
-// schedulers, so a scheduler that also hosts a long-running Fano worker warp holds the whole CTA back.  With WSPR_K4_WARPS
-// set, the CTA has fewer warps than groups of cells and each warp claims its next group from a shared counter: a slowed
-// scheduler then simply works through fewer groups.  (Which warp computes a cell does not change the cell's arithmetic.)
 __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const float *__restrict__ I, const float *__restrict__ Q,
                                                               const Job *__restrict__ jobs, const int *__restrict__ job_list,
                                                               float4 *__restrict__ P0, const float4 *__restrict__ tabs, int np,
@@ -710,23 +661,52 @@ __global__ void __launch_bounds__(LAG_THREADS, WSPR_K4_MINB) k_sync_lags(const f
         win[(m & 7) * LAG_PITCH + (m >> 3)] = v;
     }
     if (shared_tab) load_tables(tab, tabs, blockIdx.x, 2, t, LAG_THREADS);
-#if WSPR_K4_WARPS
-    __shared__ int s_next;
-    if (t == 0) s_next = 0;
-#endif
     __syncthreads();
     EXP_TIMER(0);
-#if WSPR_K4_WARPS
-    for (;;) {
-        int task = 0;
-        if ((t & 31) == 0) task = atomicAdd(&s_next, 1);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= LAG_TASKS) break;
-        lag_cell(task * 32 + (t & 31), g, blockIdx.x, win, tab, shared_tab, f0, drift, lagstep, nlags, P0, negzero, one);
+
+    const int sym_local = t / nlags, lagidx = t - sym_local * nlags;
+    const int sym = g * SYMS_PER_CTA + sym_local;
+    if (sym_local >= SYMS_PER_CTA || sym >= NSYM) return;
+    const int off = lagidx * lagstep + sym_local * SPS;     // window-relative start of this cell (multiple of 8)
+    const float2 *wp = win + (off >> 3);
+    float4 power;
+    if (shared_tab) {
+        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tab);
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
+#pragma unroll 2
+        for (int j8 = 0; j8 < SPS / 8; j8++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float2 v = wp[r * LAG_PITCH + j8];
+                const pk2 x = pk_make(v.x, v.x), y = pk_make(v.y, v.y), n = pk_make(-v.x, -v.x);
+                const ulonglong2 w01 = tp[j8 * 8 + r], w23 = tp[SPS + j8 * 8 + r];   // .x = (c,c'), .y = (s,s')
+                ai01 = pk_add(pk_add(ai01, pk_mul(x, w01.x, negzero), one), pk_mul(y, w01.y, negzero), one);
+                aq01 = pk_add(pk_add(aq01, pk_mul(n, w01.y, negzero), one), pk_mul(y, w01.x, negzero), one);
+                ai23 = pk_add(pk_add(ai23, pk_mul(x, w23.x, negzero), one), pk_mul(y, w23.y, negzero), one);
+                aq23 = pk_add(pk_add(aq23, pk_mul(n, w23.y, negzero), one), pk_mul(y, w23.x, negzero), one);
+            }
+        }
+        Acc8 a;
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
+        power = acc_power(a);
+    } else {
+        DriftPhasors ph;
+        drift_init(ph, symbol_freq(f0, drift, sym));
+        pk2 ai01 = 0, ai23 = 0, aq01 = 0, aq23 = 0;
+        for (int j8 = 0; j8 < SPS / 8; j8++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float2 v = wp[r * LAG_PITCH + j8];
+                drift_step(ai01, aq01, ai23, aq23, v.x, v.y, ph, negzero, one);
+            }
+        }
+        Acc8 a;
+        a.ai[0] = pk_lo(ai01); a.ai[1] = pk_hi(ai01); a.ai[2] = pk_lo(ai23); a.ai[3] = pk_hi(ai23);
+        a.aq[0] = pk_lo(aq01); a.aq[1] = pk_hi(aq01); a.aq[2] = pk_lo(aq23); a.aq[3] = pk_hi(aq23);
+        power = acc_power(a);
     }
-#else
-    lag_cell(t, g, blockIdx.x, win, tab, shared_tab, f0, drift, lagstep, nlags, P0, negzero, one);
-#endif
+    P0[((size_t)blockIdx.x * NSYM + sym) * MAXLAGS + lagidx] = power;    // [job][symbol][lag]: consecutive lanes, consecutive words
     EXP_STOP();
 }
 
@@ -740,17 +720,11 @@ __global__ void __launch_bounds__(64) k_pick_lag(Job *__restrict__ jobs, const i
     if (t < nlags) {
         const float4 *p = P0 + (size_t)blockIdx.x * NSYM * MAXLAGS + t;   // lane t = lag t: the lanes read consecutive words
         float ss = 0.0f, totp = 0.0f;
-        constexpr int PF = 18;                                 // 162 = 9 x 18 loads in flight: the sums themselves are serial
-        for (int i0 = 0; i0 < NSYM; i0 += PF) {
-            float4 q[PF];
-#pragma unroll
-            for (int u = 0; u < PF; u++) q[u] = p[(size_t)(i0 + u) * MAXLAGS];
-#pragma unroll
-            for (int u = 0; u < PF; u++) {
-                totp = totp + q[u].x + q[u].y + q[u].z + q[u].w;
-                float cmet = (q[u].y + q[u].w) - (q[u].x + q[u].z);
-                ss = sync_bit(i0 + u) ? ss + cmet : ss - cmet;
-            }
+        for (int i = 0; i < NSYM; i++) {
+            float4 q = p[(size_t)i * MAXLAGS];
+            totp = totp + q.x + q.y + q.z + q.w;
+            float cmet = (q.y + q.w) - (q.x + q.z);
+            ss = sync_bit(i) ? ss + cmet : ss - cmet;
         }
         v = ss / totp;
     }
@@ -1693,95 +1667,76 @@ constexpr int LPF_R = 4;                                     // consecutive outp
 #define WSPR_LPF_THREADS 256                                 // (build-time knob for A/B measurements of the CTA shape)
 #endif
 
-// A task is 128 consecutive outputs (one warp, LPF_R = 4 outputs per lane); a CTA stages the inputs of LPF_TASKS tasks.
-// LPF_TASKS == LPF_THREADS / 32: every warp computes the task of its own number (256 threads: 1024 outputs per CTA).
-// LPF_TASKS  > LPF_THREADS / 32: the warps claim tasks from a shared counter, so that a scheduler which also hosts a
-// long-running Fano warp works through fewer of them instead of holding the CTA -- its shared memory, its slots -- back
-// (see k_sync_lags); the larger tile also cuts the staging overhead (360 halo inputs per tile).
-// (One-warp CTAs of 128 outputs were tried for the same purpose: 3 % slower end to end -- 3.8x the staging traffic and 8x the CTAs.)
-#ifndef WSPR_LPF_TASKS
-#define WSPR_LPF_TASKS (WSPR_LPF_THREADS / 32)
-#endif
-template <int LPF_THREADS, int LPF_TASKS>
+// LPF_THREADS = 256: 1024 outputs per CTA.  (One-warp CTAs of 128 outputs were tried, to let a scheduler that also hosts a
+// long-running Fano warp simply take fewer of them: 3 % slower end to end -- 3.8x the staging traffic and 8x the CTAs.)
+template <int LPF_THREADS>
 __global__ void __launch_bounds__(LPF_THREADS) k_sub_lpf(float *__restrict__ I, float *__restrict__ Q,
                                                          const CapState *__restrict__ caps, const int *__restrict__ sublist,
                                                          const Counters *cnt, const float2 *__restrict__ ref,
                                                          const float2 *__restrict__ cprod, int np, int stride, pk2 negzero,
                                                          pk2 one) {
-    constexpr int LPF_TILE = LPF_TASKS * 32 * LPF_R;         // outputs per CTA
+    constexpr int LPF_TILE = LPF_THREADS * LPF_R;            // outputs per CTA
     constexpr int LPF_SPAN = LPF_TILE + NFILT;               // inputs per tile (multiple of 4)
     constexpr int LPF_PITCH = LPF_SPAN / LPF_R + 1;
-    constexpr bool DYNAMIC = LPF_TASKS != LPF_THREADS / 32;
     __shared__ __align__(8) float2 sc[LPF_R * LPF_PITCH];
-    __shared__ int s_next;
-    const int s = blockIdx.x, tile = blockIdx.y;
+    const int s = blockIdx.x, tile = blockIdx.y, t = threadIdx.x;
     if (s >= cnt->nsub) return;
     const int cap = sublist[s];
     const CapState &cs = caps[cap];
     const int i0 = tile * LPF_TILE;                          // first output (signal sample index) of the tile
     // output i needs cprod[i + NFILT/2 + tap], tap = 0..359 (cf index i+360, window starts 180 earlier)
     const float2 *src = cprod + (size_t)s * CPAD + i0 + NFILT / 2;
-    for (int m = threadIdx.x; m < LPF_SPAN; m += LPF_THREADS) {
+    for (int m = t; m < LPF_SPAN; m += LPF_THREADS) {
         int g = i0 + NFILT / 2 + m;
         sc[(m % LPF_R) * LPF_PITCH + m / LPF_R] = (g < CPAD) ? src[m] : make_float2(0.0f, 0.0f);
     }
-    if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     EXP_TIMER(1);
+    pk2 acc[LPF_R];                                          // (i, q) sums side by side (packed pairs, see pk_mul/pk_add)
+    pk2 w[LPF_R];                                            // sliding window: inputs 4t+tap .. 4t+tap+3
     const pk2 *scp = reinterpret_cast<const pk2 *>(sc);
-    for (int task = threadIdx.x >> 5;;) {
-        if (DYNAMIC) {
-            if ((threadIdx.x & 31) == 0) task = atomicAdd(&s_next, 1);
-            task = __shfl_sync(0xffffffffu, task, 0);
-        }
-        if (task >= LPF_TASKS || i0 + task * 32 * LPF_R >= NSIG) break;
-        const int t = task * 32 + (threadIdx.x & 31);        // this lane's outputs: i0 + 4t .. i0 + 4t + 3
-        pk2 acc[LPF_R];                                      // (i, q) sums side by side (packed pairs, see pk_mul/pk_add)
-        pk2 w[LPF_R];                                        // sliding window: inputs 4t+tap .. 4t+tap+3
 #pragma unroll
-        for (int r = 0; r < LPF_R; r++) {
-            acc[r] = 0;
-            w[r] = scp[r * LPF_PITCH + t];
-        }
-        for (int tap = 0; tap < NFILT; tap += LPF_R) {
+    for (int r = 0; r < LPF_R; r++) {
+        acc[r] = 0;
+        w[r] = scp[r * LPF_PITCH + t];
+    }
+    for (int tap = 0; tap < NFILT; tap += LPF_R) {
 #pragma unroll
-            for (int u = 0; u < LPF_R; u++) {
-                const float wt = c_lpf_w[tap + u];
-                const pk2 wt2 = pk_make(wt, wt);
-                // at tap+u the window holds inputs (4t + tap+u + r); rotate by u
+        for (int u = 0; u < LPF_R; u++) {
+            const float wt = c_lpf_w[tap + u];
+            const pk2 wt2 = pk_make(wt, wt);
+            // at tap+u the window holds inputs (4t + tap+u + r); rotate by u
 #pragma unroll
-                for (int r = 0; r < LPF_R; r++)               // :388-389  i += w*c.x ; q += w*c.y
-                    acc[r] = pk_add(acc[r], pk_mul(wt2, w[(u + r) % LPF_R], negzero), one);
-                // slot u now leaves the window; refill it with input 4t + tap+u + 4
-                int m = LPF_R * t + tap + u + LPF_R;
-                w[u] = scp[(m % LPF_R) * LPF_PITCH + m / LPF_R];
-            }
+            for (int r = 0; r < LPF_R; r++)                   // :388-389  i += w*c.x ; q += w*c.y
+                acc[r] = pk_add(acc[r], pk_mul(wt2, w[(u + r) % LPF_R], negzero), one);
+            // slot u now leaves the window; refill it with input 4t + tap+u + 4
+            int m = LPF_R * t + tap + u + LPF_R;
+            w[u] = scp[(m % LPF_R) * LPF_PITCH + m / LPF_R];
         }
+    }
+    float ai[LPF_R], aq[LPF_R];
 #pragma unroll
-        for (int r = 0; r < LPF_R; r++) {                     // :397-410
-            const float ai = pk_lo(acc[r]), aq = pk_hi(acc[r]);
-            int i = i0 + LPF_R * t + r;
-            if (i >= NSIG) continue;
-            float norm;
-            if (i < NFILT / 2) norm = c_lpf_psum[NFILT / 2 + i];
-            else if (i > NSIG - 1 - NFILT / 2) norm = c_lpf_psum[NFILT / 2 + NSIG - 1 - i];
-            else norm = 1.0f;
-            int k = cs.sub_shift + i;
-            if (k > 0 && k < np) {
-                float2 rr = ref[(size_t)s * NSIG + i];
-                size_t g = (size_t)cap * stride + k;
-                float di = ai * rr.x - aq * rr.y, dq = ai * rr.y + aq * rr.x;
-                if (norm != 1.0f) {                            // (x / 1.0f is x: only the two edge tiles divide)
-                    di = di / norm;
-                    dq = dq / norm;
-                }
-                I[g] = I[g] - di;
-                Q[g] = Q[g] - dq;
-            }
-        }
-        if (!DYNAMIC) break;
+    for (int r = 0; r < LPF_R; r++) {
+        ai[r] = pk_lo(acc[r]);
+        aq[r] = pk_hi(acc[r]);
     }
     EXP_STOP();
+#pragma unroll
+    for (int r = 0; r < LPF_R; r++) {                         // :397-410
+        int i = i0 + LPF_R * t + r;
+        if (i >= NSIG) continue;
+        float norm;
+        if (i < NFILT / 2) norm = c_lpf_psum[NFILT / 2 + i];
+        else if (i > NSIG - 1 - NFILT / 2) norm = c_lpf_psum[NFILT / 2 + NSIG - 1 - i];
+        else norm = 1.0f;
+        int k = cs.sub_shift + i;
+        if (k > 0 && k < np) {
+            float2 rr = ref[(size_t)s * NSIG + i];
+            size_t g = (size_t)cap * stride + k;
+            I[g] = I[g] - (ai[r] * rr.x - aq[r] * rr.y) / norm;
+            Q[g] = Q[g] - (ai[r] * rr.y + aq[r] * rr.x) / norm;
+        }
+    }
 }
 
 // grids are sized for nsub_max entries; the actual count is read from cnt->nsub on the device
@@ -1792,9 +1747,9 @@ void launch_subtract(float *I, float *Q, const CapState *caps, const int *sublis
     LAUNCHED();
     k_sub_ref<<<dim3(nsub_max, SUBREF_CTAS), SPS, 0, st>>>(I, Q, caps, sublist, cnt, phi0, ref, cprod, p.np, p.stride);
     LAUNCHED();
-    constexpr int T = WSPR_LPF_THREADS, TILE = WSPR_LPF_TASKS * 32 * LPF_R;
-    k_sub_lpf<T, WSPR_LPF_TASKS><<<dim3(nsub_max, (NSIG + TILE - 1) / TILE), T, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np,
-                                                                                         p.stride, PK_NEGZERO, PK_ONE);
+    constexpr int T = WSPR_LPF_THREADS;
+    k_sub_lpf<T><<<dim3(nsub_max, (NSIG + 4 * T - 1) / (4 * T)), T, 0, st>>>(I, Q, caps, sublist, cnt, ref, cprod, p.np, p.stride,
+                                                                             PK_NEGZERO, PK_ONE);
     LAUNCHED();
 }
 
@@ -1958,7 +1913,7 @@ void init_kernel_attributes(int carveout_kb) {
     WSPR_CARVE(k_tables); WSPR_CARVE(k_sync_lags); WSPR_CARVE(k_pick_lag); WSPR_CARVE(k_sync_freqs); WSPR_CARVE(k_sync_freqs_shared);
     WSPR_CARVE(k_pick_freq); WSPR_CARVE(k_fano_round); WSPR_CARVE(k_collect); WSPR_CARVE(k_jitter_soft); WSPR_CARVE(k_fano_enqueue);
     WSPR_CARVE(k_fano_workers); WSPR_CARVE(k_resolve); WSPR_CARVE(k_sub_phase); WSPR_CARVE(k_sub_ref);
-    WSPR_CARVE((k_sub_lpf<WSPR_LPF_THREADS, WSPR_LPF_TASKS>)); WSPR_CARVE(k_reset_caps); WSPR_CARVE(k_finish); WSPR_CARVE(k_normalise);
+    WSPR_CARVE(k_sub_lpf<WSPR_LPF_THREADS>); WSPR_CARVE(k_reset_caps); WSPR_CARVE(k_finish); WSPR_CARVE(k_normalise);
 #undef WSPR_CARVE
 }
 
