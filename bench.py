@@ -60,28 +60,57 @@ HARD = 4                                                              # message,
 
 # ---- corpus in shared memory (host, seeded; identical arrays go to the GPU path and to the CPU reference) -----------
 class SharedPlanes:
-    """float32[n, NSAMP] I and Q planes in POSIX shared memory: generator and CPU-decoder processes attach by name."""
+    """float32[n, NSAMP] I and Q planes shared with the generator and CPU-decoder processes (all forked after this object
+    exists).  POSIX shared memory, attached by name; when /dev/shm has no room for what all ranks of the node will ask for
+    (config 5 at eight ranks is 36 GB; a write into a full tmpfs kills the writer with SIGBUS and the pool would wait for
+    it forever) the planes are anonymous shared mappings instead, which the forked processes inherit."""
 
     def __init__(self, n):
+        global _INHERITED
         self.n = n
-        self.shm = [shared_memory.SharedMemory(create=True, size=max(1, n) * NSAMP * 4) for _ in range(2)]
-        self.I, self.Q = (np.ndarray((n, NSAMP), np.float32, buffer=s.buf) for s in self.shm)
-        self.names = [s.name for s in self.shm]
+        size = max(1, n) * NSAMP * 4
+        ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        try:
+            v = os.statvfs("/dev/shm")
+            room = v.f_bavail * v.f_frsize
+        except OSError:
+            room = 0
+        self.shm, self.maps = [], []
+        if os.environ.get("BENCH_ANON_SHM") == "1" or room < ranks_here * 2 * size + (1 << 30):
+            import mmap
+            self.maps = [mmap.mmap(-1, size) for _ in range(2)]
+            self.I, self.Q = (np.frombuffer(m, np.float32).reshape(max(1, n), NSAMP)[:n] for m in self.maps)
+            self.names = None
+        else:
+            self.shm = [shared_memory.SharedMemory(create=True, size=size) for _ in range(2)]
+            self.I, self.Q = (np.ndarray((n, NSAMP), np.float32, buffer=s.buf) for s in self.shm)
+            self.names = [s.name for s in self.shm]
+        _INHERITED = (self.I, self.Q)
 
     def close(self):
-        self.I = self.Q = None
+        global _INHERITED
+        self.I = self.Q = _INHERITED = None
         for s in self.shm:
             try:
                 s.close()
                 s.unlink()
             except (OSError, BufferError):
                 pass
+        for m in self.maps:
+            try:
+                m.close()
+            except (OSError, BufferError):
+                pass
 
 
 _w = {}                                              # per-process state of pool workers
+_INHERITED = None                                    # the parent's planes, as the forked workers see them
 
 
 def _attach(names, n):
+    if names is None:                                # anonymous shared mappings, inherited through fork
+        _w["I"], _w["Q"] = _INHERITED
+        return
     shm = [shared_memory.SharedMemory(name=x) for x in names]
     _w["shm"] = shm
     _w["I"], _w["Q"] = (np.ndarray((n, NSAMP), np.float32, buffer=s.buf) for s in shm)
