@@ -123,7 +123,8 @@ struct FanoService {
     FanoQueue *queue = nullptr;                    // device
     FanoQueueEntry *ring = nullptr;                // device
     std::mutex mu;
-    std::vector<std::pair<size_t, ChainScratch *>> free_scratch;   // (records, memory) returned by destroyed contexts
+    // (records, memory) returned by destroyed contexts: [0] records armed with all 43 attempts, [1] quick-mode records
+    std::vector<std::pair<size_t, ChainScratch *>> free_scratch[2];
     std::string note;
 };
 static std::mutex g_svc_mu;
@@ -229,14 +230,20 @@ static cudaError_t service_stream(FanoService *s, bool fano, cudaStream_t *out) 
     return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
 }
 
-// ChainScratch records are leased from the service and never freed while the process runs (see wspr_kernels.cuh)
-static ChainScratch *lease_scratch(FanoService *s, size_t n) {
+// ChainScratch records are leased from the service and never freed while the process runs (see wspr_kernels.cuh).
+// A worker may reach a record through an OLD ring entry (the head1 cursor lags behind while older candidates still have
+// attempts to hand out), so an idle record must never look claimable: next >= nattempts.  That holds after every hand-back
+// as long as a record is always armed with the same number of attempts -- a quick-mode candidate (attempt 0 only) leaves
+// next = 1, which is "nothing left" for 1 attempt but "42 left" the moment the record is re-armed for 43.  Quick-mode
+// decodes therefore park their candidates on records of their own (`quick` pool), leased when first needed.
+static ChainScratch *lease_scratch(FanoService *s, size_t n, int quick = 0) {
     {
         std::lock_guard<std::mutex> lock(s->mu);
-        for (size_t i = 0; i < s->free_scratch.size(); i++)
-            if (s->free_scratch[i].first >= n) {
-                ChainScratch *p = s->free_scratch[i].second;
-                s->free_scratch.erase(s->free_scratch.begin() + i);
+        auto &pool = s->free_scratch[quick ? 1 : 0];
+        for (size_t i = 0; i < pool.size(); i++)
+            if (pool[i].first >= n) {
+                ChainScratch *p = pool[i].second;
+                pool.erase(pool.begin() + i);
                 return p;
             }
     }
@@ -274,6 +281,7 @@ struct wspr_ctx {
     uint4 *moments = nullptr;      // front-end scratch of wspr_ctx_decimate: [streams][blocks] block moments
     size_t moments_cap = 0;
     ChainScratch *scratch = nullptr;   // [maxcap], leased from the service
+    ChainScratch *scratch_quick = nullptr;   // [maxcap], the records of quick-mode decodes (leased by the first one)
     int *h_done = nullptr;         // pinned, device-visible: parked captures handed back by the Fano workers so far
     char *preload = nullptr;       // device [32768][13]: hashtable.txt calls (allocated on the first -H decode)
     int *stats = nullptr;          // device [8]: how deferred candidates were settled
@@ -301,9 +309,10 @@ extern "C" void wspr_ctx_destroy(wspr_ctx *c) {
                     c->cnt, c->stats, c->preload, c->moments};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    if (c->scratch && c->svc) {
+    if (c->svc) {
         std::lock_guard<std::mutex> lock(c->svc->mu);
-        c->svc->free_scratch.push_back({(size_t)c->maxcap, c->scratch});
+        if (c->scratch) c->svc->free_scratch[0].push_back({(size_t)c->maxcap, c->scratch});
+        if (c->scratch_quick) c->svc->free_scratch[1].push_back({(size_t)c->maxcap, c->scratch_quick});
     }
     for (cudaStream_t s : c->fano_st)
         if (s) cudaStreamDestroy(s);
@@ -645,6 +654,17 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
     CK(cudaEventRecord(c->ev0, c->st));
     CK(cudaMemsetAsync(c->stats, 0, 8 * sizeof(int), c->st));
     launch_reset_caps(c->caps, ncap, o.npasses, c->st);
+    // quick-mode candidates (attempt 0 only) are parked on records of their own, see lease_scratch
+    ChainScratch *scratch = c->scratch;
+    if (p.quickmode) {
+        if (!c->scratch_quick) {
+            c->scratch_quick = lease_scratch(c->svc, (size_t)c->maxcap, 1);
+            if (!c->scratch_quick) return fail(WSPR_ERR_CUDA, "ChainScratch allocation", cudaGetLastError());
+            // (ordered before this stream's kernels; idle records, so nothing can be claimed in them meanwhile)
+            CK(cudaMemsetAsync(c->scratch_quick, 0, (size_t)c->maxcap * sizeof(ChainScratch), c->st));
+        }
+        scratch = c->scratch_quick;
+    }
     bool lingered = false;
     while (ncap > 0) {
         const int seen = *(volatile int *)c->h_done;
@@ -709,7 +729,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
                 nres_max = c->h_cnt->nres;
             }
             if (ndefer_max > 0) {                             // finish them off the critical path
-                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer_max, c->cnt, c->scratch, c->tabs, c->stats,
+                launch_deferred(c->I, c->Q, c->jobs, c->att0, c->caps, c->defer_list, ndefer_max, c->cnt, scratch, c->tabs, c->stats,
                                 c->h_done, c->svc->queue, p, c->st);
                 CK(cudaEventRecord(c->ev_fano, c->st));
                 cudaStream_t fs = c->fano_st[c->fano_rr++ % NFANO_STREAMS];

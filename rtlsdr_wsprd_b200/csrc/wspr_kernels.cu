@@ -1305,7 +1305,10 @@ struct FanoQueueFeed {
             if (overflow && !backlog()) return nullptr;
             const unsigned tail = *(volatile unsigned *)&q->tail;
             unsigned h = *(volatile unsigned *)&q->head0;
-            if (h != tail) {                                   // attempt 0 of the next candidate nobody has started
+            // (tail was read BEFORE head0: producers and other lanes may have moved both on in between, so head0 can be
+            // past the tail read here -- `!=` would then pop an entry that does not exist yet and the lane, with its whole
+            // warp, would wait for a candidate that may never come; tools/fano_queue_host_check.cpp found exactly that)
+            if ((int)(tail - h) > 0) {                         // attempt 0 of the next candidate nobody has started
                 if (atomicCAS(&q->head0, h, h + 1u) != h) continue;
                 FanoQueueEntry &x = q->ring[h & q->mask];
                 while (*(volatile unsigned *)&x.seq != h + 1u) __nanosleep(100);   // reserved, being written by a running kernel
