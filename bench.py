@@ -49,8 +49,8 @@ BYTES_PER_STREAM = 2 * N_IQ + 2 * 4 * 44992
 SYNC_BYTES_PER_CANDIDATE = (162 * 256 + 256) * 8 + 33 * 162 * 16      # IQ window read + per-(lag,symbol) tone powers written
 SYNC_FLOP_PER_CANDIDATE = 33 * 162 * 256 * 32                         # 4 tones x (4 mul + 4 add) per sample, unfused
 # dram__bytes_read.sum + dram__bytes_write.sum per candidate / per stream from the ncu --set full captures under profiles/
-SYNC_DRAM_BYTES_PER_CANDIDATE = (343.327e6 + 70.856e6) / 1024         # r1_ncu_full_packed.txt (1024 candidates per launch)
-FRONTEND_DRAM_BYTES_PER_STREAM = (2303.973e6 + 2.895e6 + 5.645e6) / 4   # r1_ncu_full_frontend.txt (4 streams per launch)
+SYNC_DRAM_BYTES_PER_CANDIDATE = (358.384e6 + 73.219e6) / 1024         # r2_ncu_full_summary.txt (1024 candidates per launch)
+FRONTEND_DRAM_BYTES_PER_STREAM = (2305.552e6 + 6.170e6 + 2.895e6) / 4   # r2_ncu_full_summary.txt (4 streams per launch)
 # unfused FP32 ceiling: measured multiply + add issue rate of tools/microbench/f32x2_bench.cu (profiles/r2_fp32_peak.txt);
 # the nominal figure is 148 SMs x 128 lanes x clock
 FP32_PEAK_FILE = os.path.join(ROOT, "profiles", "r2_fp32_peak.json")
@@ -420,7 +420,7 @@ def run_captures(args):
         roofline = {"kernel": "k_sync_lags (sync_and_demodulate mode 0)", "bound": "fp32", "achieved": round(tflops, 3),
                     "peak": round(fp32_peak, 3), "unit": "TFLOP/s", "frac": round(tflops / fp32_peak, 4),
                     "traffic": int(candidates / max(sync_launches, 1) * SYNC_DRAM_BYTES_PER_CANDIDATE),
-                    "traffic_source": "ncu --set full, profiles/r1_ncu_full_packed.txt, scaled to the mean candidates per launch",
+                    "traffic_source": "ncu --set full, profiles/r2_ncu_full_summary.txt, scaled to the mean candidates per launch",
                     "peak_source": fp32_src, "launches": sync_launches, "avg_launch_ms": round(sync_ms / max(sync_launches, 1), 4),
                     "flop_per_candidate": SYNC_FLOP_PER_CANDIDATE,
                     "note": "unfused multiplies and adds (exact-order sums rule FMA contraction out), issued as packed FFMA2 pairs; "
@@ -497,7 +497,7 @@ def measure_frontend(w, torch, local, hbm_peak, peak_src, nstreams=8):
     del raw
     return {"kernel": "k_block_moments+k_comb_fir (rtlsdr_callback)", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak,
             "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "traffic": int(nstreams * FRONTEND_DRAM_BYTES_PER_STREAM),
-            "traffic_source": "ncu --set full, profiles/r1_ncu_full_frontend.txt, scaled to the streams per launch",
+            "traffic_source": "ncu --set full, profiles/r2_ncu_full_summary.txt, scaled to the streams per launch",
             "peak_source": peak_src, "streams_per_s": round(nstreams / (ms * 1e-3), 1),
             "workload": "%d raw streams x 288e6 u8 IQ pairs resident in HBM" % nstreams}
 
@@ -685,7 +685,7 @@ def run_streams(args):
                 "roofline": {"kernel": "k_block_moments+k_comb_fir (rtlsdr_callback)", "bound": "hbm", "achieved": round(k0_gbs, 1),
                              "peak": hbm_peak, "unit": "GB/s", "frac": round(k0_gbs / hbm_peak, 4),
                              "traffic": int(chunk * FRONTEND_DRAM_BYTES_PER_STREAM * n_iq / N_IQ), "peak_source": peak_src,
-                             "traffic_source": "ncu --set full, profiles/r1_ncu_full_frontend.txt, scaled to the streams per launch",
+                             "traffic_source": "ncu --set full, profiles/r2_ncu_full_summary.txt, scaled to the streams per launch",
                              "launches": len(k0_ms), "avg_launch_ms": round(k0_total_ms / max(len(k0_ms), 1), 3),
                              "share_of_step": round(k0_total_ms / (total_ms / args.steps), 4)},
                 "cpu_baseline": None, "parity": parity, "corpus_gen_s": round(gen_s, 1)}
