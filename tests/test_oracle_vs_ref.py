@@ -215,3 +215,61 @@ def test_persistent_hashtable_option_matches_committed_golden():
     for (r, txt), g in zip(runs, gold["calls"]):
         assert H.spots_match_golden(r, g["spots"], po.spot_line), ([x["message"] for x in r], [y["message"] for y in g["spots"]])
         assert txt == g["hashtable_txt"]
+
+
+# ---- the corpora of the GPU suite (tests/test_gpu_parity.py compares the CUDA path with the ORACLE on them): the oracle
+# itself against the compiled reference on the same captures and options, so that the chain CUDA == oracle == reference
+# has no link that rests on the config-2 / config-3 recipes alone
+def _special_captures():
+    from rtlsdr_wsprd_b200 import corpus
+    caps = []
+    for c in range(2):                                                     # weak signals: jitter search, Fano time-outs
+        plan = corpus.ten_signal_plan(900 + c, snrs=np.arange(-31.0, -24.0, 1.0))
+        caps.append(("weak%d" % c, corpus.make_capture(7, 900 + c, plan, H.channel_symbols)))
+    plans = [[dict(message="K1JT FN20 20", f0=30.0, dt0=0.3, snr=-15.0, drift=-3.0)],
+             [dict(message="W1AW FN31 37", f0=-72.5, dt0=-0.9, snr=-18.0, drift=2.0)],
+             [dict(message="G4JNT IO90 10", f0=108.0, dt0=1.4, snr=-12.0)],
+             [dict(message="PJ4/K1ABC 37", f0=10.0, dt0=0.0, snr=-14.0),
+              dict(message="<PJ4/K1ABC> FK52UD 37", f0=55.0, dt0=0.1, snr=-19.0)],
+             [dict(message="K9AN EN50 33", f0=0.0, dt0=0.0, snr=-5.0), dict(message="K9AN EN50 33", f0=1.5, dt0=0.0, snr=-8.0)],
+             []]
+    for c, plan in enumerate(plans):
+        caps.append(("edge%d" % c, corpus.make_capture(8, c, plan, H.channel_symbols)))
+    z = np.zeros(corpus.NSAMP, np.float32)
+    t = np.arange(corpus.NSAMP)
+    caps.append(("zeros", (z.copy(), z.copy())))
+    caps.append(("dc", (z + np.float32(0.25), z - np.float32(0.25))))
+    caps.append(("carrier", ((0.5 * np.cos(2 * np.pi * 20.0 * t / 375.0)).astype(np.float32),
+                             (0.5 * np.sin(2 * np.pi * 20.0 * t / 375.0)).astype(np.float32))))
+    I, Q, _ = H.make_corpus(2, 2, start=40)
+    for c in range(2):
+        caps.append(("short%d" % c, (np.ascontiguousarray(I[c, :43000]), np.ascontiguousarray(Q[c, :43000]))))
+    return caps
+
+
+@needs_ref
+def test_oracle_equals_compiled_reference_on_the_gpu_suite_corpora():
+    ref, orc = po.ref(), po.oracle()
+    spots = 0
+    for name, (i, q) in _special_captures():
+        a, ia, qa = po.decode(ref, i, q)
+        b, ib, qb = po.decode(orc, i, q)
+        assert H.results_equal(a, b), (name, H.diff_results(a, b))
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb), name
+        spots += len(a)
+    assert spots >= 10
+
+
+@needs_ref
+@pytest.mark.parametrize("opt", [dict(quickmode=1), dict(subtraction=0), dict(npasses=1), dict(npasses=3), dict(npasses=4)])
+def test_oracle_equals_compiled_reference_option_variants_on_weak_signals(opt):
+    from rtlsdr_wsprd_b200 import corpus
+    ref, orc = po.ref(), po.oracle()
+    o = po.default_options(**opt)
+    for c in range(2):
+        plan = corpus.ten_signal_plan(950 + c, snrs=np.arange(-30.0, -19.0, 2.0))
+        i, q = corpus.make_capture(9, 950 + c, plan, H.channel_symbols)
+        a, ia, qa = po.decode(ref, i, q, o)
+        b, ib, qb = po.decode(orc, i, q, o)
+        assert H.results_equal(a, b), (opt, c, H.diff_results(a, b))
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb), (opt, c)
