@@ -103,8 +103,14 @@ def decode(lib, idat, qdat, options=None, cwd_scratch=True):
     (copies are made here, the mutated copies are returned).  Returns (results[RESULT_DTYPE], I', Q').
     The reference writes fftw_wisdom.dat / hashtable.txt into the CWD (wsprd.c:835,843): run in a scratch dir."""
     options = options or default_options()
-    i = np.ascontiguousarray(idat, dtype=np.float32).copy()
-    q = np.ascontiguousarray(qdat, dtype=np.float32).copy()
+    # The spectrogram loop reads samples up to index 512 * floor(n / 512) + 255 whatever n is (wsprd.c:516,536-541), i.e.
+    # up to 255 floats PAST the end when n % 512 < 256.  The reference's callers always hand over full-size, zero-tailed
+    # buffers (rtlsdr_wsprd.c:285-288,575-589), so that is what the decoder gets here too: n samples in a zero-padded buffer.
+    n_in = int(np.asarray(idat).shape[0])
+    i = np.zeros(n_in + 512, np.float32)
+    q = np.zeros(n_in + 512, np.float32)
+    i[:n_in] = idat
+    q[:n_in] = qdat
     out = (DecoderResults * MAX_UNIQUES)()
     n = C.c_int(0)
     old = os.getcwd()
@@ -113,13 +119,13 @@ def decode(lib, idat, qdat, options=None, cwd_scratch=True):
         if scratch:
             os.chdir(scratch)
         lib.wspr_decode(i.ctypes.data_as(C.POINTER(C.c_float)), q.ctypes.data_as(C.POINTER(C.c_float)),
-                        int(i.shape[0]), options, out, C.byref(n))
+                        n_in, options, out, C.byref(n))
     finally:
         os.chdir(old)
         if scratch:
             shutil.rmtree(scratch, ignore_errors=True)
     arr = np.frombuffer(bytes(out), dtype=RESULT_DTYPE, count=MAX_UNIQUES)[: n.value].copy()
-    return arr, i, q
+    return arr, i[:n_in].copy(), q[:n_in].copy()
 
 
 def spot_line(r):

@@ -273,3 +273,21 @@ def test_oracle_equals_compiled_reference_option_variants_on_weak_signals(opt):
         b, ib, qb = po.decode(orc, i, q, o)
         assert H.results_equal(a, b), (opt, c, H.diff_results(a, b))
         assert np.array_equal(ia, ib) and np.array_equal(qa, qb), (opt, c)
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [44700, 44032, 38400, 31400])
+def test_short_captures_whose_last_block_reaches_past_the_end(n):
+    """blocks = 4 * floor(n / 512) - 1 and block i covers samples 128 i .. 128 i + 511 (wsprd.c:516,536-541): with
+    n % 512 < 256 the last blocks read up to 255 samples past n.  The reference's callers hand over full-size buffers with a
+    zeroed tail (rtlsdr_wsprd.c:285-288,575-589); pyoracle.decode does the same for both CPU decoders, and the CUDA path
+    reads zeros there as well (a context's sample rows are zeroed when it is created and never written past n)."""
+    assert n % 512 < 256
+    I, Q, _ = H.make_corpus(3, 1, start=7)
+    i, q = np.ascontiguousarray(I[0, :n]), np.ascontiguousarray(Q[0, :n])
+    a, ia, qa = po.decode(po.ref(), i, q)
+    b, ib, qb = po.decode(po.oracle(), i, q)
+    assert len(a) >= 5 and H.results_equal(a, b), H.diff_results(a, b)
+    assert ia.shape == (n,) and np.array_equal(ia, ib) and np.array_equal(qa, qb)
+    again, _, _ = po.decode(po.ref(), i, q)                       # (deterministic: nothing depends on what follows the buffer)
+    assert H.results_equal(a, again)
