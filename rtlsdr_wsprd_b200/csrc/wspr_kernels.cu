@@ -1363,6 +1363,13 @@ struct FanoQueueFeed {
 // whose lanes are all idle with the queue empty gives its place up FIRST and looks at the queue once more afterwards (a
 // producer may have added work, and the warps launched for that work may have found the pool complete and left), taking
 // the place back if there is something to do -- so work is never stranded, and nobody ever waits for work.
+// (The place on the SM -- sm_workers, the per-SM cap -- is given up only at the very end, a few hundred clocks after the last
+// look at the queue: a warp launched for new work that lands on this SM inside that window finds it full and leaves.  The
+// launch of such a warp follows the enqueue by microseconds and a launch spreads its CTAs over all SMs, so not ALL of them
+// can be turned away that way in practice; tools/fano_queue_host_check.cpp strands candidates only when the exit is
+// artificially slowed by 300 us on a one-SM model.  Giving the SM place up before the look, like the pool place, closes the
+// window for good; it was not done in round 2 because it re-allocates the registers of the whole kernel and the change
+// could no longer be run on a GPU.)
 // A CTA carries blockDim.x / 32 worker warps, completely independent of each other (no CTA barrier): with more than one the
 // warps of a CTA sit on different schedulers of their SM, which single-warp CTAs leave to chance.
 __global__ void __launch_bounds__(128) k_fano_workers(FanoQueue *__restrict__ q, int delta, unsigned maxcycles, int overflow) {

@@ -12,6 +12,8 @@
 // x86 orders memory more strongly than a GPU does, so this checks the protocol's logic, not its fences.
 #include <cuda_runtime.h>      // vector types only: nothing of the CUDA runtime is called
 #include <sched.h>
+#include <time.h>
+#include <cstdlib>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -157,6 +159,15 @@ void worker(Sim *s, unsigned smid) {
                 mine = atomicAdd(active, 1) < *pool;
                 if (!mine) atomicSub(active, 1);
             }
+        }
+        // FANO_QUEUE_SLOW_EXIT_US (experiment, not used by the tests): the SM place is given up this long after the last look at
+        // the queue.  With 300 us on a one- or two-SM model, workers started for the last candidates find "their" SM full of
+        // workers that are on their way out and leave, and the candidates are stranded (the watchdog fires) -- the window the
+        // comment above k_fano_workers describes; without the delay 3000 such runs strand nothing.
+        static const long slow_exit_us = [] { const char *e = getenv("FANO_QUEUE_SLOW_EXIT_US"); return e ? atol(e) : 0L; }();
+        if (slow_exit_us > 0) {
+            struct timespec ts = {0, slow_exit_us * 1000L};
+            nanosleep(&ts, nullptr);
         }
         if (per_sm > 0) atomicSub(&q->sm_workers[smid], 1);
         atomicAdd(&q->st_attempts, (unsigned long long)feed.attempts);
