@@ -532,12 +532,24 @@ static void linger_parked(wspr_ctx *c, int seen, int want) {
     }
 }
 // every open capture is parked: sleep until at least one has been handed back, then linger for more
-static int wait_parked(wspr_ctx *c, int seen, int want) {
+static int wait_parked(wspr_ctx *c, int seen, int want, const DecodeParams &p) {
     const volatile int *done = c->h_done;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (unsigned spin = 0; *done == seen; spin++) {
         if ((spin & 1023u) == 1023u) {             // (a failed kernel would otherwise leave us here for good)
             cudaError_t e = cudaStreamQuery(c->fano_st[0]);
             if (e != cudaSuccess && e != cudaErrorNotReady) return fail(WSPR_ERR_CUDA, "Fano workers", e);
+            // belt and braces: nothing has come back for a quarter of a second (a hopeless attempt alone takes 0.1-0.2 s, so
+            // this is rare but legitimate) -- start a few workers.  They leave at once if the pool is complete or the queue
+            // empty; if candidates were ever left in the queue with nobody alive to work on them (the window described
+            // above k_fano_workers), this is what picks them up.
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if ((t1.tv_sec - t0.tv_sec) * 1000L + (t1.tv_nsec - t0.tv_nsec) / 1000000L >= 250) {
+                launch_fano_workers(c->svc->queue, 4, c->svc->cta_warps, false, p, c->fano_st[c->fano_rr++ % NFANO_STREAMS]);
+                CK(cudaGetLastError());
+                t0 = t1;
+            }
         }
         if (wait_blocks()) usleep(50);
         else sched_yield();
@@ -681,7 +693,7 @@ extern "C" int wspr_ctx_decode(wspr_ctx *c, decoder_options o) {
         }
         if (h.ndone == ncap) break;
         if (h.nsetup == 0 && h.njobs == 0 && h.nres == 0) {   // everything still open is parked with the Fano workers
-            if (wait_parked(c, seen, std::min(h.nwait, 64))) return WSPR_ERR_CUDA;
+            if (wait_parked(c, seen, std::min(h.nwait, 64), p)) return WSPR_ERR_CUDA;
             continue;
         }
         // a handful of captures ready while many more are with the pool: give those a moment to come back and plan again
