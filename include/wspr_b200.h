@@ -59,7 +59,10 @@ struct decoder_results {
 /* ================= 1. reference entry points ================= */
 /* wsprd/wsprd.h:106-111.  idat/qdat (host, `samples` floats each) are mutated by the signal subtraction exactly like
  * the reference does; decodes must hold WSPR_MAX_UNIQUES entries.  Always returns 0 like the reference; on a CUDA
- * failure *n_results is set to 0 and the error is printed to stderr. */
+ * failure *n_results is set to 0 and the error is printed to stderr.
+ * Only `samples` floats are read: where the reference's spectrogram loop reaches past the end of a short capture (up to
+ * 255 samples when samples % 512 < 256, wsprd.c:516,536-541) this library reads zeros, which is what the reference itself
+ * finds there in its own program (full-size buffers with a zeroed tail, rtlsdr_wsprd.c:285-288,575-589). */
 int wspr_decode(float *idat, float *qdat, int samples, struct decoder_options options,
                 struct decoder_results *decodes, int *n_results);
 /* wsprd/wsprd.h:76-91 */
