@@ -15,7 +15,7 @@ import helpers as H
 SUBSET = ("reference_fixture or golden_option_variants or weak_signals_exercise or drifting_and_edge or degenerate or short_capture "
           "or persistent_hashtable_option or fano_kernel or sync_and_demodulate_abi or subtract_signal2_abi "
           "or subtract_signal_abi or stage_spectrogram or frontend_against_reference_golden or frontend_ragged "
-          "or streaming_frontend or one_shot_batch_entry")
+          "or streaming_frontend or one_shot_batch_entry or quick_and_normal")
 
 
 @pytest.fixture(scope="module")

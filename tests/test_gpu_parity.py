@@ -568,3 +568,30 @@ def test_sharded_decode_on_two_gpus(tmp_path):
     for c in range(7):
         a, _, _ = po.decode(po.oracle(), I[c], Q[c])
         assert H.results_equal(a, spots[c, : n[c]]), (c, H.diff_results(a, spots[c, : n[c]]))
+
+
+def test_quick_and_normal_decodes_alternate_on_one_context():
+    """One context decodes the same weak-signal captures in quick mode, in normal mode and in quick mode again: candidates
+    are parked in all three (quick mode parks an unfinished jitter-0 attempt with ONE attempt, normal mode with 43), on the
+    context's two sets of scratch records (lease_scratch in wspr_decode.cu), and every decode equals the oracle's."""
+    n = 3
+    I = np.zeros((n, corpus.NSAMP), np.float32)
+    Q = np.zeros_like(I)
+    for c in range(n):
+        plan = corpus.ten_signal_plan(970 + c, snrs=np.arange(-31.0, -22.0, 1.5))
+        I[c], Q[c] = corpus.make_capture(9, 970 + c, plan, H.channel_symbols)
+    want = {}
+    for quick in (1, 0):
+        want[quick] = [po.decode(po.oracle(), I[c], Q[c], po.default_options(quickmode=quick)) for c in range(n)]
+    parked = 0
+    with w.BatchDecoder(n, corpus.NSAMP) as d:
+        for quick in (1, 0, 1, 0):
+            d.upload(I, Q)
+            d.decode(w.default_options(quickmode=quick))
+            spots, cnt, Io, Qo = d.download(samples=True)
+            parked += d.schedule_stats()[1]
+            for c in range(n):
+                a, ia, qa = want[quick][c]
+                assert H.results_equal(a, spots[c, : cnt[c]]), (quick, c, H.diff_results(a, spots[c, : cnt[c]]))
+                assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c]), (quick, c)
+    assert parked > 0, "no candidate was parked: the corpus does not exercise the scratch records"
