@@ -15,8 +15,9 @@ from transpile import transpile  # noqa: E402
 SOURCES = ["wspr_kernels", "wspr_decode", "wspr_frontend", "wspr_abi"]
 
 
-def build(outdir, opt="-O2", jobs=4):
-    csrc = os.path.join(ROOT, "rtlsdr_wsprd_b200", "csrc")
+def build(outdir, opt="-O2", defs=(), csrc=None):
+    """defs: extra -D options (the build-time variants of the kernels); csrc: another copy of the csrc directory (a patched one)"""
+    csrc = csrc or os.path.join(ROOT, "rtlsdr_wsprd_b200", "csrc")
     dst = os.path.join(outdir, "rtlsdr_wsprd_b200", "csrc")
     os.makedirs(dst, exist_ok=True)
     os.makedirs(os.path.join(outdir, "include"), exist_ok=True)
@@ -36,7 +37,7 @@ def build(outdir, opt="-O2", jobs=4):
                 text = transpile(f.read())
             with open(os.path.join(dst, name[:-3] + ".cpp"), "w") as f:
                 f.write(text)
-    flags = ["g++", opt, "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=default", "-w", "-I" + HERE, "-I" + dst]
+    flags = ["g++", opt, "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=default", "-w", "-I" + HERE, "-I" + dst] + list(defs)
     objs, procs = [], []
     for name in SOURCES:
         obj = os.path.join(dst, name + ".o")
@@ -58,4 +59,11 @@ def build(outdir, opt="-O2", jobs=4):
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1] if len(sys.argv) > 1 else "/tmp/wspr_b200_emu"))
+    # python tools/cuda_emu/build.py <outdir> [-DNAME=VALUE ...] [--csrc DIR]
+    args = sys.argv[1:]
+    other = None
+    if "--csrc" in args:
+        k = args.index("--csrc")
+        other = args[k + 1]
+        del args[k:k + 2]
+    print(build(args[0] if args and not args[0].startswith("-D") else "/tmp/wspr_b200_emu", defs=[a for a in args if a.startswith("-D")], csrc=other))
