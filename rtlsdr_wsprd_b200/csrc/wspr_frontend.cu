@@ -63,7 +63,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {        // read-once
 #define PACK4(a, b, c, d) ((int)(((unsigned)(a)&255u) | (((unsigned)(b)&255u) << 8) | (((unsigned)(c)&255u) << 16) | (((unsigned)(d)&255u) << 24)))
 
 struct Moments {
-    int s0i, s0q, s1i, s1q;
+    unsigned s0i, s0q, s1i, s1q;                   // sums over Z/2^32 (the reference's int32 integrators wrap, rtlsdr_wsprd.c:130-135,192-195)
 };
 
 __device__ __forceinline__ unsigned neg_byte3(unsigned u) { return (u ^ 0xff000000u) + 0x01000000u; }
@@ -86,18 +86,18 @@ __device__ __forceinline__ void accumulate_vector(Moments &m, const uint4 v, int
     aq = dp4a_us(z, PACK4(0, 1, 1, 0), aq);
     aq = dp4a_us(w, PACK4(0, 1, 1, 0), aq);
     // first moment about the vector's first sample (offsets 0..7; -128 * 28 = -3584), accumulated straight into S1
-    int bi = dp4a_us(x, PACK4(0, 0, 0, 1), m.s1i - 3584);
+    int bi = dp4a_us(x, PACK4(0, 0, 0, 1), (int)(m.s1i - 3584u));
     bi = dp4a_us(y, PACK4(2, 0, 0, 3), bi);
     bi = dp4a_us(z, PACK4(4, 0, 0, 5), bi);
     bi = dp4a_us(w, PACK4(6, 0, 0, 7), bi);
-    int bq = dp4a_us(x, PACK4(0, 0, 1, 0), m.s1q - 3584);
+    int bq = dp4a_us(x, PACK4(0, 0, 1, 0), (int)(m.s1q - 3584u));
     bq = dp4a_us(y, PACK4(0, 2, 3, 0), bq);
     bq = dp4a_us(z, PACK4(0, 4, 5, 0), bq);
     bq = dp4a_us(w, PACK4(0, 6, 7, 0), bq);
-    m.s0i += ai;
-    m.s0q += aq;
-    m.s1i = t0 * ai + bi;
-    m.s1q = t0 * aq + bq;
+    m.s0i += (unsigned)ai;                         // (unsigned: wrap-around is the arithmetic here, not an accident)
+    m.s0q += (unsigned)aq;
+    m.s1i = (unsigned)t0 * (unsigned)ai + (unsigned)bi;
+    m.s1q = (unsigned)t0 * (unsigned)aq + (unsigned)bq;
 }
 
 // force the bytes of a vector that lie outside [lo, hi) (byte offsets relative to the vector start) to 128

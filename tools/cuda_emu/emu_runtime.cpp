@@ -47,6 +47,11 @@ Block g_block;
 ucontext_t g_main;
 const std::function<void()> *g_body = nullptr;
 Fiber *g_fiber = nullptr;
+const int g_order = [] {
+    const char *e = getenv("EMU_ORDER");
+    return !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r' && e[1] == 'a') ? 2 : 0;
+}();
+unsigned long long g_rng = 0x853c49e6748fea9bull;
 
 char *stack_for(size_t i) {
     while (g_stacks.size() <= i) {
@@ -190,8 +195,16 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
                 }
                 for (Warp &w : b.warps)
                     for (int l = w.alive; l < 32; l++) w.active[l] = false;
+                // EMU_ORDER=reverse | random: the fibers of a CTA are resumed in another order than 0, 1, 2, ... -- results that
+                // change with it point at a missing barrier (threads reading what other threads wrote in the same phase)
                 while (b.alive > 0) {
-                    for (int t = 0; t < nthreads; t++) {
+                    for (int k = 0; k < nthreads; k++) {
+                        int t = k;
+                        if (g_order == 1) t = nthreads - 1 - k;
+                        else if (g_order == 2) {
+                            g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+                            t = (int)((g_rng >> 33) % (unsigned)nthreads);
+                        }
                         Fiber &f = g_fibers[t];
                         if (f.done) continue;
                         g_fiber = &f;
