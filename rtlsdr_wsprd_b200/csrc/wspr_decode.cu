@@ -546,6 +546,10 @@ static int wait_parked(wspr_ctx *c, int seen, int want, const DecodeParams &p) {
             // above k_fano_workers), this is what picks them up.
             clock_gettime(CLOCK_MONOTONIC, &t1);
             if ((t1.tv_sec - t0.tv_sec) * 1000L + (t1.tv_nsec - t0.tv_nsec) / 1000000L >= 250) {
+                // (a ring that has overflowed has lost candidates: their captures would never come back)
+                int overflow = 0;
+                CK(cudaMemcpy(&overflow, &c->svc->queue->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+                if (overflow) return fail(WSPR_ERR_CUDA, "Fano queue overflow: parked candidates were lost");
                 launch_fano_workers(c->svc->queue, 4, c->svc->cta_warps, false, p, c->fano_st[c->fano_rr++ % NFANO_STREAMS]);
                 CK(cudaGetLastError());
                 t0 = t1;
