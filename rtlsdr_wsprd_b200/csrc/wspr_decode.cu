@@ -339,7 +339,10 @@ static int ctx_init(wspr_ctx *c, int device, int maxcap, int samples) {
     c->device = device;
     c->maxcap = maxcap;
     c->np = samples;
-    c->stride = (samples + 127) / 128 * 128;
+    // a row holds the capture and, zeroed, whatever the spectrogram reads past its end: block i covers samples 128 i .. 128 i + 511
+    // and there are 4 floor(samples / 512) - 1 blocks, so the last one ends at 512 floor(samples / 512) + 255 -- beyond a
+    // capture whose length is below 256 modulo 512 (wsprd.c:516,536-541; the reference's buffers are full-size and zero-tailed)
+    c->stride = (std::max(samples, NFFT * (samples / NFFT) + NFFT / 2) + 127) / 128 * 128;
     c->blocks = 4 * (samples / NFFT) - 1;                    // wsprd.c:516
     c->svc = fano_service(device);
     if (!c->svc) return fail(WSPR_ERR_CUDA, "Fano service set-up failed", cudaGetLastError());
