@@ -20,8 +20,6 @@ MSGS = ["K1JT FN20 20", "VA2GKA FN35 37", "W1AW FN31 30", "G4JNT IO90 10", "PJ4/
         "<K1JT> FN20AB 20", "DL1ABC JO62 23", "JA1XYZ PM95 27", "ZL3GHI RE66 0", "EA4PQR IN80 60", "VK2DEF QF56 3", "K9AN EN50 33"]
 
 
-def one(seed):")[0].split('"""', 2)[2])
-
 def one(seed):
     import rtlsdr_wsprd_b200 as w
     rng = np.random.default_rng(seed)
