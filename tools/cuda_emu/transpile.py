@@ -107,6 +107,7 @@ def rewrite_launches(s):
         grid, block = cfg[0], cfg[1]
         smem = cfg[2] if len(cfg) > 2 else "0"
         new = "emu::launch(emu::d3(%s), emu::d3(%s), (size_t)(%s), [&]() { %s(%s); })" % (grid, block, smem, name, args)
+        new = new.replace("\n", " ") + "\n" * s.count("\n", j + 1, b + 1)     # (line numbers stay those of the .cu file)
         s = s[:j + 1] + new + s[b + 1:]
 
 
@@ -183,7 +184,7 @@ def rewrite_asm(s):
         if repl is None:
             repl = 'emu::unsupported_asm("%s");' % template.replace("\\", "\\\\").replace('"', '\\"')[:200]
         out.append(s[pos:m.start()])
-        out.append(repl)
+        out.append(repl.replace("\n", " ") + "\n" * s.count("\n", m.start(), semi + 1))
         pos = semi + 1
     out.append(s[pos:])
     return "".join(out)
@@ -202,7 +203,7 @@ def transpile(text):
     text = rewrite_extern_shared(text)
     text = rewrite_asm(text)
     text = rewrite_launches(text)
-    return '#include "cuda_runtime.h"\n' + text
+    return '#include "cuda_runtime.h"  // (kept on line 1: the line numbers below are those of the original file)\n' + text.split("\n", 1)[1] if text.startswith("//") or text.startswith("\n") else '#include "cuda_runtime.h"\n' + text
 
 
 if __name__ == "__main__":
