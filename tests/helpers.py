@@ -24,6 +24,41 @@ def channel_symbols(msg, lib=None):
     return np.frombuffer(bytes(sym), np.uint8).copy()
 
 
+def symbols_from_packed(n, m, lib=None):
+    """162 channel symbols from the packed 28-bit callsign field n and 22-bit grid/power field m, the tail of
+    get_wspr_channel_symbols (wsprsim_utils.c:262-316): 50 bits -> 11 bytes -> convolutional code -> interleave -> 2 * bit + sync.
+    For messages the text interface refuses to encode although the decoder produces them."""
+    lib = lib or po.oracle()
+    data = (C.c_ubyte * 11)()
+    data[0], data[1], data[2] = (n >> 20) & 255, (n >> 12) & 255, (n >> 4) & 255
+    data[3], data[4], data[5], data[6] = ((n & 15) << 4) | ((m >> 18) & 15), (m >> 10) & 255, (m >> 2) & 255, (m & 3) << 6
+    bits = (C.c_ubyte * 176)()
+    lib.encode(bits, data, 11)
+    chan = (C.c_ubyte * 162)(*bits[:162])
+    lib.interleave(chan)
+    sync = channel_symbols("K1JT FN20 20", lib) & 1              # the sync vector is the low bit of every channel symbol
+    return (2 * np.frombuffer(bytes(chan), np.uint8) + sync).astype(np.uint8)
+
+
+def break_captures(lib=None):
+    """Two captures that make the reference leave its candidate loop early (wsprd.c:781-793): the strongest signal, examined
+    first in pass 0, decodes to a message that (a) get_wspr_channel_symbols cannot encode again for the subtraction -- a
+    type-1 message with a three-character callsign -- or (b) carries the locator 'A000AA'; two ordinary signals follow and
+    are never reached, and with no unique decode pass 1 does not run (wsprd.c:521-522): the result is empty."""
+    lib = lib or po.oracle()
+    lib.pack_call.restype = C.c_ulong
+    lib.pack_grid4_power.restype = C.c_ulong
+    grid = (C.c_char * 5)(*[bytes([lib.get_locator_character_code(C.c_char(ch.encode()))]) for ch in "FN20"])
+    special = {"three-character callsign": symbols_from_packed(int(lib.pack_call(b"A1A")), int(lib.pack_grid4_power(grid, 20)), lib),
+               "locator A000AA": channel_symbols("<K1JT> A000AA 23", lib)}
+    out = []
+    for k, (name, sym) in enumerate(special.items()):
+        plan = [dict(message="SPECIAL", f0=-40.0, dt0=0.0, snr=-5.0), dict(message="K1JT FN20 20", f0=20.0, dt0=0.2, snr=-12.0),
+                dict(message="W1AW FN31 30", f0=70.0, dt0=-0.3, snr=-14.0)]
+        out.append((name, corpus.make_capture(91, 1 + k, plan, lambda msg, s=sym: s if msg == "SPECIAL" else channel_symbols(msg, lib))))
+    return out
+
+
 def make_corpus(config, count, start=0):
     return corpus.make_corpus(config, count, channel_symbols, start=start)
 

@@ -600,3 +600,17 @@ def test_quick_and_normal_decodes_alternate_on_one_context():
                 assert H.results_equal(a, spots[c, : cnt[c]]), (quick, c, H.diff_results(a, spots[c, : cnt[c]]))
                 assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c]), (quick, c)
     assert parked > 0, "no candidate was parked: the corpus does not exercise the scratch records"
+
+
+def test_candidate_loop_breaks():
+    """The reference's two early exits from the candidate loop (wsprd.c:781-793): a decoded message that cannot be encoded
+    again for the subtraction, and the locator 'A000AA' (helpers.break_captures).  The capture's pass ends there (CapState::
+    broken), nothing has been recorded yet, so pass 1 does not run either: no spots, samples untouched -- like the oracle,
+    with and without the subtraction."""
+    caps = H.break_captures()
+    I = np.stack([c[1][0] for c in caps])
+    Q = np.stack([c[1][1] for c in caps])
+    spots, n, Io, Qo = gpu_decode(I, Q)
+    assert list(n) == [0, 0]
+    assert_batch_equals_oracle(I, Q)
+    assert assert_batch_equals_oracle(I, Q, subtraction=0) >= 3

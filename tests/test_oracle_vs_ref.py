@@ -291,3 +291,19 @@ def test_short_captures_whose_last_block_reaches_past_the_end(n):
     assert ia.shape == (n,) and np.array_equal(ia, ib) and np.array_equal(qa, qb)
     again, _, _ = po.decode(po.ref(), i, q)                       # (deterministic: nothing depends on what follows the buffer)
     assert H.results_equal(a, again)
+
+
+@needs_ref
+def test_candidate_loop_breaks_oracle_equals_reference():
+    """The two `break`s of the candidate loop (wsprd.c:781-793, helpers.break_captures): nothing is decoded, in both."""
+    for name, (i, q) in H.break_captures():
+        a, ia, qa = po.decode(po.ref(), i, q)
+        b, ib, qb = po.decode(po.oracle(), i, q)
+        assert len(a) == 0 and H.results_equal(a, b), (name, H.spot_lines(a), H.spot_lines(b))
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb), name
+        # the same capture without the special signal's consequences: with subtraction off nothing is re-encoded, no break (a)
+        c, _, _ = po.decode(po.ref(), i, q, po.default_options(subtraction=0))
+        d, _, _ = po.decode(po.oracle(), i, q, po.default_options(subtraction=0))
+        assert H.results_equal(c, d), name
+        if name == "three-character callsign":
+            assert len(c) == 3, H.spot_lines(c)
