@@ -600,6 +600,9 @@ def test_quick_and_normal_decodes_alternate_on_one_context():
                 assert H.results_equal(a, spots[c, : cnt[c]]), (quick, c, H.diff_results(a, spots[c, : cnt[c]]))
                 assert np.array_equal(ia, Io[c]) and np.array_equal(qa, Qo[c]), (quick, c)
     assert parked > 0, "no candidate was parked: the corpus does not exercise the scratch records"
+    st = w.fano_pool_stats()                                      # the pool's counters (wspr_fano_stats)
+    assert st["pool_warps"] >= 1 and st["worker_warps_started"] >= 1 and st["attempts_run"] + st["attempts_dropped"] > 0
+    assert 0.0 < st["lane_utilisation"] <= 1.0
 
 
 def test_candidate_loop_breaks():
@@ -614,3 +617,48 @@ def test_candidate_loop_breaks():
     assert list(n) == [0, 0]
     assert_batch_equals_oracle(I, Q)
     assert assert_batch_equals_oracle(I, Q, subtraction=0) >= 3
+
+
+def _device_bytes(a):
+    """A device copy of a uint8 array -> (keep-alive object, device pointer).  Under the host emulation (tools/cuda_emu)
+    device pointers are host pointers and there is no CUDA for torch to use."""
+    import torch
+    if torch.cuda.is_available():
+        t = torch.from_numpy(a).cuda()
+        torch.cuda.synchronize()
+        return t, t.data_ptr()
+    assert "emu" in os.path.basename(w.library_path()), "no CUDA device and not the emulated build"
+    return a, a.ctypes.data
+
+
+def test_context_decimate_normalise_decode_chain():
+    """Raw streams that are already on the device go through the front end straight into a context (wspr_ctx_decimate: the
+    callback for whole streams, tail zeroed, rtlsdr_wsprd.c:126-244,285-288), are peak-normalised there (:291-305) and decoded
+    (:316) -- the chain bench.py's config 4 runs.  Every stage against the oracle."""
+    nstreams, n_iq = 3, 6401 * 70 + 2000
+    stride = (2 * n_iq + 15) // 16 * 16 + 16
+    rng = np.random.default_rng(4)
+    raw = np.zeros((nstreams, stride), np.uint8)
+    raw[:, : 2 * n_iq] = np.clip(127.5 + 30 * rng.standard_normal((nstreams, 2 * n_iq)), 0, 255).astype(np.uint8)
+    raw[1, 4000:9000] = 0                                                  # a stretch on the rail: the int8 -(-128) wrap
+    keep, ptr = _device_bytes(raw)
+    orc = po.oracle()
+    orc.oracle_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    with w.BatchDecoder(nstreams, corpus.NSAMP) as d:
+        assert d.decimate(ptr, nstreams, n_iq, stride) is not None
+        _, _, I1, Q1 = d.download(samples=True)
+        want = []
+        for s in range(nstreams):
+            io, qo = np.zeros(corpus.NSAMP, np.float32), np.zeros(corpus.NSAMP, np.float32)
+            n = orc.oracle_decimate(raw[s].ctypes.data, n_iq, io.ctypes.data, qo.ctypes.data, corpus.NSAMP)
+            assert n == 70
+            assert np.array_equal(I1[s], io) and np.array_equal(Q1[s], qo), s          # 70 outputs, then zeros
+            want.append(po.normalise_half(io, qo))
+        d.normalise()
+        d.decode()
+        spots, cnt, I2, Q2 = d.download(samples=True)
+        for s in range(nstreams):
+            a, ia, qa = po.decode(orc, want[s][0], want[s][1])
+            assert H.results_equal(a, spots[s, : cnt[s]]), (s, H.diff_results(a, spots[s, : cnt[s]]))
+            assert np.array_equal(ia, I2[s]) and np.array_equal(qa, Q2[s]), s
+    del keep
