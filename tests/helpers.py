@@ -45,9 +45,10 @@ def break_captures(lib=None):
     first in pass 0, decodes to a message that (a) get_wspr_channel_symbols cannot encode again for the subtraction -- a
     type-1 message with a three-character callsign -- or (b) carries the locator 'A000AA'; two ordinary signals follow and
     are never reached, and with no unique decode pass 1 does not run (wsprd.c:521-522): the result is empty."""
-    lib = lib or po.oracle()
+    lib = C.CDLL((lib or po.oracle())._name)                     # (a private handle: return types are set on it below)
     lib.pack_call.restype = C.c_ulong
     lib.pack_grid4_power.restype = C.c_ulong
+    lib.get_locator_character_code.restype = C.c_ubyte
     grid = (C.c_char * 5)(*[bytes([lib.get_locator_character_code(C.c_char(ch.encode()))]) for ch in "FN20"])
     special = {"three-character callsign": symbols_from_packed(int(lib.pack_call(b"A1A")), int(lib.pack_grid4_power(grid, 20)), lib),
                "locator A000AA": channel_symbols("<K1JT> A000AA 23", lib)}
