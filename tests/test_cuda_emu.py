@@ -32,7 +32,9 @@ def emulated_library(tmp_path_factory):
 
 
 def test_gpu_parity_subset_on_the_emulated_build(emulated_library):
-    env = dict(os.environ, WSPR_B200_LIB=emulated_library)
+    # (EMU_DEFER_WORKERS: the worker pool's launches run late, so parked captures stay parked across rounds and the host's
+    # waiting / lingering / relaunching paths run as they do next to a GPU; results must not depend on it)
+    env = dict(os.environ, WSPR_B200_LIB=emulated_library, EMU_DEFER_WORKERS="2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(H.ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                         "-p", "no:cacheprovider", "-k", SUBSET], capture_output=True, text=True, env=env, cwd=H.ROOT, timeout=3000)
     tail = r.stdout[-3000:] + r.stderr[-1500:]

@@ -55,7 +55,8 @@ struct ThreadState {
     int lane, warp;
 };
 extern ThreadState *g_cur;                                   // the fiber that is running
-void launch(dim3 grid, dim3 block, size_t dynamic_smem, const std::function<void()> &body);
+void launch(const char *kernel, dim3 grid, dim3 block, size_t dynamic_smem, const std::function<void()> &body);
+void run_deferred(bool from_query);                          // EMU_DEFER_WORKERS: the worker-pool launches that were put off
 void syncthreads();
 void syncwarp();
 void yield();
@@ -173,7 +174,7 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { emu::run_deferred(false); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof *p);
     strcpy(p->name, "host emulation");
@@ -221,7 +222,7 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
 static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { return cudaStreamCreate(s); }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { emu::run_deferred(true); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent_{0}; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }

@@ -155,9 +155,50 @@ void unsupported_asm(const char *what) {
     abort();
 }
 
-void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &body) {
-    std::lock_guard<std::mutex> lock(g_launch_mu);
+// EMU_DEFER_WORKERS=n: launches of k_fano_workers do not run at once but when the host has polled cudaStreamQuery n times since
+// the first of them (wait_parked does so every 1024 spins) or synchronises the device -- the worker pool then lags behind the
+// rounds as it does on a GPU: captures stay parked (PH_WAIT) across rounds, the host lingers and waits for hand-backs, and
+// with n large enough it reaches its quarter-second relaunch.  Results must not depend on any of it.
+struct Deferred {
+    dim3 grid, block;
+    size_t smem;
+    std::function<void()> body;
+};
+std::vector<Deferred> g_deferred;
+std::mutex g_deferred_mu;
+int g_queries_since_deferral = 0;
+const int g_defer_workers = [] {
+    const char *e = getenv("EMU_DEFER_WORKERS");
+    return e ? atoi(e) : 0;
+}();
+
+static void run_now(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &body);
+
+void run_deferred(bool from_query) {
+    std::vector<Deferred> todo;
+    {
+        std::lock_guard<std::mutex> lock(g_deferred_mu);
+        if (g_deferred.empty()) return;
+        if (from_query && ++g_queries_since_deferral < g_defer_workers) return;
+        todo.swap(g_deferred);
+        g_queries_since_deferral = 0;
+    }
+    for (Deferred &d : todo) run_now(d.grid, d.block, d.smem, d.body);
+}
+
+void launch(const char *kernel, dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &body) {
+    if (g_defer_workers > 0 && strcmp(kernel, "k_fano_workers") == 0) {
+        std::lock_guard<std::mutex> lock(g_deferred_mu);
+        g_deferred.push_back(Deferred{grid, block, dynamic_smem_bytes, body});
+        g_launches++;
+        return;
+    }
     g_launches++;
+    run_now(grid, block, dynamic_smem_bytes, body);
+}
+
+static void run_now(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &body) {
+    std::lock_guard<std::mutex> lock(g_launch_mu);
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads <= 0 || nthreads > 1024 || dynamic_smem_bytes > DYN_SMEM_BYTES) {
         fprintf(stderr, "cuda_emu: launch configuration out of range (%d threads, %zu bytes of dynamic shared memory)\n", nthreads,

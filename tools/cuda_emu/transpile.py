@@ -106,7 +106,8 @@ def rewrite_launches(s):
         args = s[a + 1:b]
         grid, block = cfg[0], cfg[1]
         smem = cfg[2] if len(cfg) > 2 else "0"
-        new = "emu::launch(emu::d3(%s), emu::d3(%s), (size_t)(%s), [&]() { %s(%s); })" % (grid, block, smem, name, args)
+        # (arguments captured by value: a launch may be deferred, see EMU_DEFER_WORKERS in emu_runtime.cpp)
+        new = 'emu::launch("%s", emu::d3(%s), emu::d3(%s), (size_t)(%s), [=]() { %s(%s); })' % (name, grid, block, smem, name, args)
         new = new.replace("\n", " ") + "\n" * s.count("\n", j + 1, b + 1)     # (line numbers stay those of the .cu file)
         s = s[:j + 1] + new + s[b + 1:]
 
