@@ -207,9 +207,18 @@ static void run_now(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std:
     }
     if ((int)g_fibers.size() < nthreads) g_fibers.resize(nthreads);
     g_body = &body;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    // (EMU_ORDER=reverse | random also applies to the CTAs of a grid: lists that kernels build with atomics come out in
+    // another order, which no result may depend on)
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    std::vector<unsigned long long> order(nblocks);
+    for (unsigned long long i = 0; i < nblocks; i++) order[i] = g_order == 1 ? nblocks - 1 - i : i;
+    if (g_order == 2)
+        for (unsigned long long i = nblocks; i > 1; i--) {
+            g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(order[i - 1], order[(g_rng >> 33) % i]);
+        }
+    for (unsigned long long idx : order) {
+                const unsigned bx = (unsigned)(idx % grid.x), by = (unsigned)((idx / grid.x) % grid.y), bz = (unsigned)(idx / ((unsigned long long)grid.x * grid.y));
                 Block &b = g_block;
                 b.nthreads = b.alive = nthreads;
                 b.bar_arrived = 0;
